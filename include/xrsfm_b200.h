@@ -1,0 +1,239 @@
+/*
+ * xrsfm_b200.h — C ABI of the B200-native engine behind XRSfM's two hot paths.
+ *
+ * Plain C: pointers + sizes only, no C++/torch types.  Every entry point names the
+ * reference interface it replaces (paths relative to the openxrlab/xrsfm tree).
+ *
+ *   path M (matching):  xrsfm::FeatureMatching -> SiftMatch(uint8) -> SiftMatchGPU
+ *                       src/feature/feature_processing.cc:118-154,222-308
+ *                       3rdparty/SiftGPU/SiftGPU.h:277-372, SiftMatchCU.cpp:55-215
+ *   path B (bundle adj): xrsfm::BASolver::{GBA,KGBA,LBA} -> ceres::Solve
+ *                       src/optimization/ba_solver.h:14-30, ba_solver.cc:330-391,523-678
+ *
+ * All functions return XRB_OK (0) or a negative xrb_status unless stated otherwise;
+ * xrb_last_error() gives a thread-local message for the last failure.
+ * The library fails loudly (XRB_ERR_NO_DEVICE) when no sm_100 GPU is usable:
+ * there is no CPU fallback behind this ABI.
+ */
+#ifndef XRSFM_B200_H_
+#define XRSFM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XRB_ABI_VERSION 1
+
+typedef enum xrb_status {
+    XRB_OK = 0,
+    XRB_ERR_INVALID = -1,   /* bad argument */
+    XRB_ERR_NO_DEVICE = -2, /* no CUDA device / wrong architecture */
+    XRB_ERR_CUDA = -3,      /* CUDA runtime error (SiftMatchCU.cpp:209-212 returns -1) */
+    XRB_ERR_CAPACITY = -4,  /* caller buffer too small; sizes were still reported */
+    XRB_ERR_NUMERIC = -5,   /* BA: non-finite step / factorisation breakdown */
+    XRB_ERR_COMM = -6       /* BA multi-GPU: exchange hook failed */
+} xrb_status;
+
+int xrb_abi_version(void);
+const char *xrb_last_error(void);
+/* number of kernels this library has launched in the calling process so far */
+uint64_t xrb_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------ */
+/* Path M — SIFT descriptor matching                                   */
+/* ------------------------------------------------------------------ */
+
+typedef struct xrb_matcher xrb_matcher;
+
+/* Replaces SiftMatchGPU::SiftMatchGPU(int) + SetLanguage(CUDA_DEVICE0+device) +
+ * VerifyContextGL() + Allocate(max_features, mbm)  (SiftGPU.h:307-324,
+ * feature_processing.cc:53-88).  max_features is rounded up to a multiple of 32
+ * like SiftMatchCU::SetMaxSift (SiftMatchCU.cpp:84-87).  Returns NULL on failure. */
+xrb_matcher *xrb_match_create(int max_features, int device);
+void xrb_match_destroy(xrb_matcher *m);
+int xrb_match_max_features(const xrb_matcher *m);
+
+/* Per-pair compatibility surface ------------------------------------ */
+
+/* Replaces SiftMatchGPU::SetDescriptors(int index, int num, const unsigned char*, int id)
+ * (SiftGPU.h:331-334, SiftMatchCU.cpp:100-118).  `desc` is a HOST pointer to
+ * num x 128 row-major uint8 (src/base/types.h:9-10).  index is clamped to {0,1},
+ * num is clamped to max_features, id != -1 && id == previous id skips the upload. */
+int xrb_match_set_descriptors(xrb_matcher *m, int index, int num, const uint8_t *desc,
+                              int id);
+
+/* Replaces SiftMatchGPU::GetSiftMatch (SiftGPU.h:337-343, SiftMatchCU.cpp:175-215).
+ * Returns the number of matches written to match_buffer (ascending first index,
+ * truncated at max_match), 0 if a set is empty, or -1 on a CUDA error — the
+ * reference's own convention. */
+int xrb_match_get(xrb_matcher *m, int max_match, uint32_t (*match_buffer)[2],
+                  float distmax, float ratiomax, int mutual_best_match);
+
+/* Batched surface (what a replacement FeatureMatching uses) ---------- */
+
+/* Make the descriptors of n_images images resident in HBM.  counts[i] features for
+ * image i (clamped to max_features), descs[i] = HOST pointer to counts[i] x 128 uint8.
+ * Replaces the per-pair H2D copies of feature_processing.cc:136-137. */
+int xrb_match_upload_images(xrb_matcher *m, int n_images, const int32_t *counts,
+                            const uint8_t *const *descs);
+
+/* Same, from one contiguous HOST block: image i starts at row offsets[i] (rows of
+ * 128 bytes), offsets has n_images+1 entries. */
+int xrb_match_upload_packed(xrb_matcher *m, int n_images, const int64_t *row_offsets,
+                            const uint8_t *desc_block);
+
+/* Same, but the block is already DEVICE memory (no copy is made; the caller keeps it
+ * alive).  Used to measure the HBM-resident path. */
+int xrb_match_attach_device(xrb_matcher *m, int n_images, const int64_t *row_offsets_host,
+                            const uint8_t *desc_block_device);
+
+/* Match n_pairs image pairs (indices into the uploaded set), HOST in / HOST out.
+ * out_offsets has n_pairs+1 entries (prefix sums of per-pair match counts);
+ * matches of pair p are out[out_offsets[p] .. out_offsets[p+1]) as (idx1, idx2),
+ * each list exactly what SiftMatchCU::GetBestMatch would have produced for that pair
+ * (SiftMatchCU.cpp:186-215).  out_capacity is in matches; on XRB_ERR_CAPACITY
+ * out_offsets is still valid.  Semantics per pair: feature_processing.cc:118-154. */
+int xrb_match_pairs(xrb_matcher *m, int n_pairs, const int32_t (*pairs)[2], float distmax,
+                    float ratiomax, int mutual_best_match, int max_match,
+                    int64_t *out_offsets, uint32_t (*out)[2], int64_t out_capacity);
+
+/* Device-resident variant: pairs_dev, counts_dev[n_pairs], out_dev are DEVICE pointers;
+ * matches of pair p go to out_dev[p*out_stride ...]; work is enqueued on `stream`
+ * (a cudaStream_t, may be NULL) and NOT synchronised. */
+int xrb_match_pairs_device(xrb_matcher *m, int n_pairs, const int32_t (*pairs_dev)[2],
+                           float distmax, float ratiomax, int mutual_best_match,
+                           int max_match, int32_t *counts_dev, uint32_t (*out_dev)[2],
+                           int out_stride, void *stream);
+
+/* Test hook (no reference counterpart): float(acos(double(min(float(v)*2^-18,1)))) for
+ * v = 0..n-1 as CUDA computes it, so the CPU oracle's libm can be checked over the whole
+ * domain of ProgramCU.cu:1830-1831. out is a HOST array. */
+int xrb_match_debug_dist_table(float *out_host, int n);
+
+/* Which kernel generation a matcher runs: 0 = auto (best available), 1 = dp4a tiles,
+ * 2 = tcgen05.  Returns the variant now in force. */
+int xrb_match_set_variant(xrb_matcher *m, int variant);
+
+/* ------------------------------------------------------------------ */
+/* Path B — bundle adjustment                                          */
+/* ------------------------------------------------------------------ */
+
+typedef struct xrb_ba_solver xrb_ba_solver;
+
+/* Flat (SoA) restatement of what BASolver::SetUp builds per observation
+ * (ba_solver.cc:330-356): residual block (q[4], t[3], X[3], intrinsics[K]). */
+typedef struct xrb_ba_problem {
+    int32_t n_cams, n_pts, n_obs, n_intr;
+    double *cam_q;             /* [4*n_cams] Eigen coeffs order x,y,z,w; in/out   */
+    double *cam_t;             /* [3*n_cams] in/out                               */
+    double *pts;               /* [3*n_pts]  in/out                               */
+    const double *intr;        /* [8*n_intr] camera params, padded to 8           */
+    const int32_t *intr_model; /* [n_intr] model id 0..4 (camera_model.hpp:93-210)*/
+    const int32_t *cam_intr;   /* [n_cams] -> intrinsics index                    */
+    const int32_t *obs_cam;    /* [n_obs]                                         */
+    const int32_t *obs_pt;     /* [n_obs]                                         */
+    const double *obs_uv;      /* [2*n_obs] measured pixel                        */
+    const uint8_t *cam_q_fixed; /* [n_cams] or NULL: SetParameterBlockConstant(q) */
+    const uint8_t *cam_t_fixed; /* [n_cams] or NULL: ba_solver.cc:611-614         */
+    const uint8_t *pt_fixed;    /* [n_pts]  or NULL: ba_solver.cc:380-382         */
+} xrb_ba_problem;
+
+/* ceres::Solver::Options fields the reference sets (ba_solver.cc:70-77,624-634,
+ * 665-670) plus the cost-functor constants (cost_factor_ceres.h:29-31, ba_solver.cc:343). */
+typedef struct xrb_ba_options {
+    int32_t max_iterations;     /* 50 GBA accurate / 20 otherwise / 5 LBA */
+    double function_tolerance;  /* 1e-5 / 1e-4                            */
+    double parameter_tolerance; /* 1e-6 / 1e-5                            */
+    double gradient_tolerance;  /* 1e-10 (Ceres default)                  */
+    double initial_radius;      /* 1e4 (Ceres default) / 1e6 KGBA         */
+    double huber_a;             /* 5.99                                   */
+    double min_depth;           /* 1e-2                                   */
+    double neg_depth_residual;  /* 12.0                                   */
+    int32_t verbose;            /* minimizer_progress_to_stdout           */
+    int32_t fixed_iterations;   /* !=0: run exactly max_iterations LM iterations,
+                                   ignoring the tolerance tests (bench only) */
+} xrb_ba_options;
+
+enum {
+    XRB_BA_CONVERGENCE = 0,    /* ceres::CONVERGENCE    */
+    XRB_BA_NO_CONVERGENCE = 1, /* ceres::NO_CONVERGENCE */
+    XRB_BA_FAILURE = 2         /* ceres::FAILURE        */
+};
+
+typedef struct xrb_ba_iteration {
+    int32_t iteration;
+    int32_t step_is_valid, step_is_successful;
+    double cost;               /* cost after this iteration (incl. fixed cost) */
+    double cost_change;        /* x_cost - candidate_cost                      */
+    double gradient_max_norm;
+    double step_norm;
+    double relative_decrease;  /* rho                                          */
+    double trust_region_radius;
+    double model_cost_change;
+} xrb_ba_iteration;
+
+/* The fields PrintSolverSummary reads (ba_solver.cc:14-68). */
+typedef struct xrb_ba_summary {
+    int32_t num_residuals_reduced;
+    int32_t num_effective_parameters_reduced;
+    int32_t num_successful_steps, num_unsuccessful_steps;
+    int32_t termination_type;
+    double initial_cost, final_cost, fixed_cost;
+    double total_time_in_seconds;
+    double linear_solver_seconds, residual_seconds; /* device-event split */
+    int32_t n_iterations_logged; /* entries valid in `iterations` (incl. iteration 0);
+                                    like Ceres, an iteration that ends on a tolerance test
+                                    is not logged and its step is discarded */
+    int32_t num_lm_iterations;   /* passes through the LM loop executed = linear solves,
+                                    incl. the terminating one: the unit of the metric */
+    xrb_ba_iteration iterations[128];
+} xrb_ba_summary;
+
+void xrb_ba_default_options(xrb_ba_options *opt); /* Ceres defaults + xrsfm constants */
+
+xrb_ba_solver *xrb_ba_create(int device);
+void xrb_ba_destroy(xrb_ba_solver *s);
+
+/* Multi-GPU exchange hook.  With world > 1 each rank owns a shard of the points (all
+ * their observations) and a full replica of the cameras; once per linear solve the
+ * solver calls `allreduce(buf_dev, count, user)` — an in-place SUM over ranks of
+ * `count` doubles in DEVICE memory, enqueued on `stream` of xrb_ba_solve — on the packed
+ * [reduced camera system | rhs | column norms | scalars] buffer.  Typical hook:
+ * ncclAllReduce(ncclDouble, ncclSum) or torch.distributed.all_reduce.  Must return 0. */
+typedef int (*xrb_allreduce_fn)(void *buf_dev, size_t count, void *user);
+int xrb_ba_set_exchange(xrb_ba_solver *s, int rank, int world, xrb_allreduce_fn fn,
+                        void *user);
+
+/* Replaces ceres::Solve at ba_solver.cc:591,636,672 (problem build included): HOST
+ * arrays in, poses/points updated in place, summary filled.  In multi-GPU mode every
+ * rank passes the FULL problem and the solver keeps only its shard of the points
+ * (balanced by sum k_p^2); all ranks return the same poses and points. */
+int xrb_ba_solve(xrb_ba_solver *s, const xrb_ba_problem *prob, const xrb_ba_options *opt,
+                 xrb_ba_summary *summary);
+
+/* Split form, used to time the HBM-resident inner loop: load() uploads and builds the
+ * point-major CSR, run() iterates on the device state (may be called repeatedly after
+ * reset()), fetch() copies poses/points back into the problem's host arrays. */
+int xrb_ba_load(xrb_ba_solver *s, const xrb_ba_problem *prob);
+int xrb_ba_reset(xrb_ba_solver *s); /* restore the state uploaded by load() */
+int xrb_ba_run(xrb_ba_solver *s, const xrb_ba_options *opt, xrb_ba_summary *summary,
+               void *stream);
+int xrb_ba_fetch(xrb_ba_solver *s, xrb_ba_problem *prob);
+
+/* Per-observation residuals (after the depth branch, before the loss) at the current
+ * device state, in the caller's observation order: out[2*n_obs] HOST.  This is
+ * ReProjectionCost::operator() (cost_factor_ceres.h:19-40) over the whole problem. */
+int xrb_ba_residuals(xrb_ba_solver *s, double *out_residuals);
+
+/* Last-run device timings in milliseconds: [0] linearise+Schur, [1] reduced system
+ * factor+solve, [2] back-substitution+update, [3] cost evaluation, [4] exchange,
+ * [5] whole run; and launches of each (same indices). */
+int xrb_ba_profile(const xrb_ba_solver *s, double ms[6], int64_t launches[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XRSFM_B200_H_ */

@@ -1,0 +1,383 @@
+// match_api.cu — C ABI of path M (see include/xrsfm_b200.h for the reference lines each
+// entry point replaces).  Host logic only: buffer ownership, batching, copies.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "match_kernels.cuh"
+
+using namespace xrb;
+
+struct xrb_matcher {
+    int device = 0;
+    int max_features = 4096;
+    int variant = 1;  // generation in force
+    cudaStream_t stream = nullptr;
+
+    // resident image set
+    DevBuf images;                  // owned descriptor block (when uploaded from host)
+    const uint8_t *block = nullptr; // device pointer actually used (owned or attached)
+    std::vector<int64_t> offsets;   // n_images + 1 row offsets (host copy)
+    DevBuf offsets_dev;
+    int n_images = 0;
+
+    // per-pair compatibility slots (SiftMatchCU::_texDes[2], SiftMatchCU.cpp:100-118)
+    DevBuf slot[2];
+    int slot_n[2] = {0, 0};
+    int slot_id[2] = {0, 0};  // SiftMatchCU.cpp:50 initialises _id_sift to 0
+
+    // batch scratch
+    int chunk_pairs = 0, state_stride = 0;
+    DevBuf rows_best, rows_second, cols_best, cols_second;
+    DevBuf pairdesc, counts, strided, packed, pack_offsets, vlow, pair_idx;
+    int strided_stride = 0;
+};
+
+namespace {
+
+int ensure_scratch(xrb_matcher *m, int n_pairs_hint) {
+    // Size the batch so the top-2 state stays below ~512 MiB.
+    const int stride = m->max_features;
+    const size_t per_pair = (size_t)stride * (8 + 4) * 2;
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>(2048, (512ull << 20) / per_pair));
+    chunk = std::min(chunk, std::max(1, n_pairs_hint));
+    if (chunk <= m->chunk_pairs && stride == m->state_stride) return XRB_OK;
+    chunk = std::max(chunk, m->chunk_pairs);
+    const size_t n = (size_t)chunk * stride;
+    int rc;
+    if ((rc = m->rows_best.reserve(n * 8))) return rc;
+    if ((rc = m->cols_best.reserve(n * 8))) return rc;
+    if ((rc = m->rows_second.reserve(n * 4))) return rc;
+    if ((rc = m->cols_second.reserve(n * 4))) return rc;
+    XRB_CUDA(cudaMemsetAsync(m->rows_best.p, 0, n * 8, m->stream));
+    XRB_CUDA(cudaMemsetAsync(m->cols_best.p, 0, n * 8, m->stream));
+    XRB_CUDA(cudaMemsetAsync(m->rows_second.p, 0, n * 4, m->stream));
+    XRB_CUDA(cudaMemsetAsync(m->cols_second.p, 0, n * 4, m->stream));
+    if ((rc = m->pairdesc.reserve((size_t)chunk * sizeof(PairDesc)))) return rc;
+    if ((rc = m->counts.reserve((size_t)chunk * 4))) return rc;
+    if ((rc = m->pack_offsets.reserve((size_t)(chunk + 1) * 8))) return rc;
+    if ((rc = m->vlow.reserve(16))) return rc;
+    m->chunk_pairs = chunk;
+    m->state_stride = stride;
+    return XRB_OK;
+}
+
+int score(xrb_matcher *m, const PairDesc *pd_dev, int n, int max_n1, int max_n2,
+          cudaStream_t st) {
+    Top2State rows{m->rows_best.as<unsigned long long>(), m->rows_second.as<unsigned int>()};
+    Top2State cols{m->cols_best.as<unsigned long long>(), m->cols_second.as<unsigned int>()};
+    if (m->variant == 2)
+        return launch_score_tc(pd_dev, n, max_n1, max_n2, m->state_stride, rows, cols,
+                               m->vlow.as<int>(), st);
+    return launch_score_dp4a(pd_dev, n, max_n1, max_n2, m->state_stride, rows, cols,
+                             m->vlow.as<int>(), st);
+}
+
+int finalize(xrb_matcher *m, const PairDesc *pd_dev, int n, float distmax, float ratiomax,
+             int mbm, int max_match, int32_t *counts_dev, uint32_t (*out_dev)[2],
+             int out_stride, cudaStream_t st) {
+    Top2State rows{m->rows_best.as<unsigned long long>(), m->rows_second.as<unsigned int>()};
+    Top2State cols{m->cols_best.as<unsigned long long>(), m->cols_second.as<unsigned int>()};
+    return launch_finalize(pd_dev, n, m->state_stride, rows, cols, distmax, ratiomax, mbm,
+                           max_match, counts_dev, out_dev, out_stride, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+xrb_matcher *xrb_match_create(int max_features, int device) {
+    if (select_device(device) != XRB_OK) return nullptr;
+    xrb_matcher *m = new xrb_matcher();
+    m->device = device;
+    // SiftMatchCU ctor / SetMaxSift round up to a multiple of 32 (SiftMatchCU.cpp:47-53,84-87)
+    m->max_features = max_features <= 0 ? 4096 : ((max_features + 31) / 32) * 32;
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        delete m;
+        return nullptr;
+    }
+    m->variant = score_tc_available() ? 2 : 1;
+    return m;
+}
+
+void xrb_match_destroy(xrb_matcher *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaStreamSynchronize(m->stream);
+    DevBuf *bufs[] = {&m->images, &m->offsets_dev, &m->slot[0], &m->slot[1], &m->rows_best,
+                      &m->rows_second, &m->cols_best, &m->cols_second, &m->pairdesc,
+                      &m->counts, &m->strided, &m->packed, &m->pack_offsets, &m->vlow,
+                      &m->pair_idx};
+    for (DevBuf *b : bufs) b->release();
+    cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+int xrb_match_max_features(const xrb_matcher *m) { return m ? m->max_features : 0; }
+
+int xrb_match_set_variant(xrb_matcher *m, int variant) {
+    if (!m) return XRB_ERR_INVALID;
+    if (variant == 0) variant = score_tc_available() ? 2 : 1;
+    if (variant == 2 && !score_tc_available()) variant = 1;
+    if (variant != 1 && variant != 2) {
+        set_error("unknown matcher variant %d", variant);
+        return XRB_ERR_INVALID;
+    }
+    m->variant = variant;
+    return variant;
+}
+
+int xrb_match_set_descriptors(xrb_matcher *m, int index, int num, const uint8_t *desc,
+                              int id) {
+    if (!m) return XRB_ERR_INVALID;
+    XRB_CUDA(cudaSetDevice(m->device));
+    index = index > 1 ? 1 : (index < 0 ? 0 : index);  // SiftMatchCU.cpp:104-107
+    if (id != -1 && id == m->slot_id[index]) return XRB_OK;  // :110-111
+    m->slot_id[index] = id;
+    if (num > m->max_features) num = m->max_features;  // :113-114
+    if (num < 0) num = 0;
+    m->slot_n[index] = num;
+    if (num == 0) return XRB_OK;
+    if (!desc) {
+        set_error("set_descriptors: null descriptor pointer");
+        return XRB_ERR_INVALID;
+    }
+    int rc = m->slot[index].reserve((size_t)m->max_features * kDim);
+    if (rc) return rc;
+    XRB_CUDA(cudaMemcpyAsync(m->slot[index].p, desc, (size_t)num * kDim,
+                             cudaMemcpyHostToDevice, m->stream));
+    return XRB_OK;
+}
+
+int xrb_match_get(xrb_matcher *m, int max_match, uint32_t (*match_buffer)[2], float distmax,
+                  float ratiomax, int mutual_best_match) {
+    if (!m) return 0;
+    if (m->slot_n[0] <= 0 || m->slot_n[1] <= 0) return 0;  // SiftMatchCU.cpp:179-180
+    if (max_match <= 0) return 0;
+    if (cudaSetDevice(m->device) != cudaSuccess) return -1;
+    if (ensure_scratch(m, 1) != XRB_OK) return -1;
+    const int n1 = m->slot_n[0], n2 = m->slot_n[1];
+    const int stride = std::min(max_match, n1);
+    if (m->strided.reserve((size_t)stride * 8) != XRB_OK) return -1;
+    PairDesc pd{m->slot[0].as<uint8_t>(), m->slot[1].as<uint8_t>(), n1, n2};
+    cudaStream_t st = m->stream;
+    if (cudaMemcpyAsync(m->pairdesc.p, &pd, sizeof pd, cudaMemcpyHostToDevice, st) !=
+        cudaSuccess)
+        return -1;
+    if (launch_vlow(distmax, ratiomax, m->vlow.as<int>(), st)) return -1;
+    if (score(m, m->pairdesc.as<PairDesc>(), 1, n1, n2, st)) return -1;
+    if (finalize(m, m->pairdesc.as<PairDesc>(), 1, distmax, ratiomax, mutual_best_match,
+                 max_match, m->counts.as<int32_t>(), m->strided.as<uint32_t[2]>(), stride, st))
+        return -1;
+    int32_t n = 0;
+    if (cudaMemcpyAsync(&n, m->counts.p, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) {  // SiftMatchCU.cpp:209-212
+        set_error("matcher: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    if (n > 0 &&
+        cudaMemcpy(match_buffer, m->strided.p, (size_t)n * 8, cudaMemcpyDeviceToHost) !=
+            cudaSuccess)
+        return -1;
+    return n;
+}
+
+static int set_offsets(xrb_matcher *m, int n_images, const int64_t *row_offsets) {
+    m->offsets.assign(row_offsets, row_offsets + n_images + 1);
+    m->n_images = n_images;
+    int rc = m->offsets_dev.reserve((size_t)(n_images + 1) * 8);
+    if (rc) return rc;
+    XRB_CUDA(cudaMemcpyAsync(m->offsets_dev.p, m->offsets.data(), (size_t)(n_images + 1) * 8,
+                             cudaMemcpyHostToDevice, m->stream));
+    XRB_CUDA(cudaStreamSynchronize(m->stream));
+    return XRB_OK;
+}
+
+int xrb_match_upload_images(xrb_matcher *m, int n_images, const int32_t *counts,
+                            const uint8_t *const *descs) {
+    if (!m || n_images < 0 || (n_images && (!counts || !descs))) {
+        set_error("upload_images: bad arguments");
+        return XRB_ERR_INVALID;
+    }
+    XRB_CUDA(cudaSetDevice(m->device));
+    std::vector<int64_t> off(n_images + 1, 0);
+    for (int i = 0; i < n_images; ++i) {
+        if (counts[i] < 0) {
+            set_error("upload_images: negative count for image %d", i);
+            return XRB_ERR_INVALID;
+        }
+        off[i + 1] = off[i] + counts[i];
+    }
+    int rc = m->images.reserve(std::max<size_t>(16, (size_t)off[n_images] * kDim));
+    if (rc) return rc;
+    for (int i = 0; i < n_images; ++i)
+        if (counts[i])
+            XRB_CUDA(cudaMemcpyAsync(m->images.as<uint8_t>() + off[i] * kDim, descs[i],
+                                     (size_t)counts[i] * kDim, cudaMemcpyHostToDevice,
+                                     m->stream));
+    m->block = m->images.as<uint8_t>();
+    return set_offsets(m, n_images, off.data());
+}
+
+int xrb_match_upload_packed(xrb_matcher *m, int n_images, const int64_t *row_offsets,
+                            const uint8_t *desc_block) {
+    if (!m || n_images < 0 || !row_offsets || (row_offsets[n_images] && !desc_block)) {
+        set_error("upload_packed: bad arguments");
+        return XRB_ERR_INVALID;
+    }
+    XRB_CUDA(cudaSetDevice(m->device));
+    const size_t bytes = (size_t)row_offsets[n_images] * kDim;
+    int rc = m->images.reserve(std::max<size_t>(16, bytes));
+    if (rc) return rc;
+    if (bytes)
+        XRB_CUDA(cudaMemcpyAsync(m->images.p, desc_block, bytes, cudaMemcpyHostToDevice,
+                                 m->stream));
+    m->block = m->images.as<uint8_t>();
+    return set_offsets(m, n_images, row_offsets);
+}
+
+int xrb_match_attach_device(xrb_matcher *m, int n_images, const int64_t *row_offsets_host,
+                            const uint8_t *desc_block_device) {
+    if (!m || n_images < 0 || !row_offsets_host || !desc_block_device) {
+        set_error("attach_device: bad arguments");
+        return XRB_ERR_INVALID;
+    }
+    XRB_CUDA(cudaSetDevice(m->device));
+    m->block = desc_block_device;
+    return set_offsets(m, n_images, row_offsets_host);
+}
+
+int xrb_match_pairs_device(xrb_matcher *m, int n_pairs, const int32_t (*pairs_dev)[2],
+                           float distmax, float ratiomax, int mutual_best_match,
+                           int max_match, int32_t *counts_dev, uint32_t (*out_dev)[2],
+                           int out_stride, void *stream) {
+    if (!m || n_pairs < 0 || !m->block) {
+        set_error("pairs_device: no images resident / bad arguments");
+        return XRB_ERR_INVALID;
+    }
+    if (n_pairs == 0) return XRB_OK;
+    XRB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_scratch(m, n_pairs);
+    if (rc) return rc;
+    if (m->stream != st) XRB_CUDA(cudaStreamSynchronize(m->stream));  // scratch memsets
+    if (out_stride < std::min(max_match, m->max_features)) {
+        // every pair may legitimately produce min(max_match, n1) matches
+        int64_t worst = 0;
+        for (int i = 0; i < m->n_images; ++i)
+            worst = std::max<int64_t>(worst, m->offsets[i + 1] - m->offsets[i]);
+        worst = std::min<int64_t>(std::min<int64_t>(worst, m->max_features), max_match);
+        if (out_stride < worst) {
+            set_error("pairs_device: out_stride %d < worst-case matches %lld", out_stride,
+                      (long long)worst);
+            return XRB_ERR_CAPACITY;
+        }
+    }
+    if (launch_vlow(distmax, ratiomax, m->vlow.as<int>(), st)) return XRB_ERR_CUDA;
+    int64_t max_n = 0;
+    for (int i = 0; i < m->n_images; ++i)
+        max_n = std::max<int64_t>(max_n, m->offsets[i + 1] - m->offsets[i]);
+    const int max_feat = (int)std::min<int64_t>(max_n, m->max_features);
+    for (int p0 = 0; p0 < n_pairs; p0 += m->chunk_pairs) {
+        const int n = std::min(m->chunk_pairs, n_pairs - p0);
+        PairDesc *pd = m->pairdesc.as<PairDesc>();
+        if ((rc = launch_build_pairs(pairs_dev + p0, n, m->offsets_dev.as<int64_t>(), m->block,
+                                     m->max_features, pd, st)))
+            return rc;
+        if ((rc = score(m, pd, n, max_feat, max_feat, st))) return rc;
+        if ((rc = finalize(m, pd, n, distmax, ratiomax, mutual_best_match, max_match,
+                           counts_dev + p0, out_dev + (size_t)p0 * out_stride, out_stride, st)))
+            return rc;
+    }
+    return XRB_OK;
+}
+
+int xrb_match_pairs(xrb_matcher *m, int n_pairs, const int32_t (*pairs)[2], float distmax,
+                    float ratiomax, int mutual_best_match, int max_match,
+                    int64_t *out_offsets, uint32_t (*out)[2], int64_t out_capacity) {
+    if (!m || n_pairs < 0 || !out_offsets || (n_pairs && !pairs) || !m->block) {
+        set_error("match_pairs: no images resident / bad arguments");
+        return XRB_ERR_INVALID;
+    }
+    out_offsets[0] = 0;
+    if (n_pairs == 0) return XRB_OK;
+    for (int p = 0; p < n_pairs; ++p)
+        if (pairs[p][0] < 0 || pairs[p][0] >= m->n_images || pairs[p][1] < 0 ||
+            pairs[p][1] >= m->n_images) {
+            set_error("match_pairs: pair %d references image outside [0,%d)", p, m->n_images);
+            return XRB_ERR_INVALID;
+        }
+    XRB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    int rc = ensure_scratch(m, n_pairs);
+    if (rc) return rc;
+    int64_t max_n = 0;
+    for (int i = 0; i < m->n_images; ++i)
+        max_n = std::max<int64_t>(max_n, m->offsets[i + 1] - m->offsets[i]);
+    const int max_feat = (int)std::min<int64_t>(max_n, m->max_features);
+    const int stride = std::max(1, std::min(max_match, max_feat));
+    const int chunk = m->chunk_pairs;
+    if ((rc = m->strided.reserve((size_t)chunk * stride * 8))) return rc;
+    if ((rc = m->packed.reserve((size_t)chunk * stride * 8))) return rc;
+    if ((rc = m->pair_idx.reserve((size_t)chunk * 8))) return rc;
+    if (launch_vlow(distmax, ratiomax, m->vlow.as<int>(), st)) return XRB_ERR_CUDA;
+
+    std::vector<int64_t> chunk_off(chunk + 1);
+    int64_t total = 0;
+    bool overflow = false;
+    for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
+        const int n = std::min(chunk, n_pairs - p0);
+        XRB_CUDA(cudaMemcpyAsync(m->pair_idx.p, pairs + p0, (size_t)n * 8,
+                                 cudaMemcpyHostToDevice, st));
+        PairDesc *pd = m->pairdesc.as<PairDesc>();
+        if ((rc = launch_build_pairs(m->pair_idx.as<int32_t[2]>(), n,
+                                     m->offsets_dev.as<int64_t>(), m->block, m->max_features,
+                                     pd, st)))
+            return rc;
+        if ((rc = score(m, pd, n, max_feat, max_feat, st))) return rc;
+        if ((rc = finalize(m, pd, n, distmax, ratiomax, mutual_best_match, max_match,
+                           m->counts.as<int32_t>(), m->strided.as<uint32_t[2]>(), stride, st)))
+            return rc;
+        if ((rc = launch_pack(m->counts.as<int32_t>(), n, m->strided.as<uint32_t[2]>(), stride,
+                              m->pack_offsets.as<int64_t>(), m->packed.as<uint32_t[2]>(), 0,
+                              (int64_t)chunk * stride, st)))
+            return rc;
+        XRB_CUDA(cudaMemcpyAsync(chunk_off.data(), m->pack_offsets.p, (size_t)(n + 1) * 8,
+                                 cudaMemcpyDeviceToHost, st));
+        XRB_CUDA(cudaStreamSynchronize(st));
+        const int64_t got = chunk_off[n];
+        for (int k = 0; k < n; ++k) out_offsets[p0 + k + 1] = total + chunk_off[k + 1];
+        if (total + got <= out_capacity && out) {
+            if (got)
+                XRB_CUDA(cudaMemcpyAsync(out + total, m->packed.p, (size_t)got * 8,
+                                         cudaMemcpyDeviceToHost, st));
+        } else {
+            overflow = true;
+        }
+        total += got;
+    }
+    XRB_CUDA(cudaStreamSynchronize(st));
+    if (overflow) {
+        set_error("match_pairs: out_capacity %lld < %lld matches", (long long)out_capacity,
+                  (long long)total);
+        return XRB_ERR_CAPACITY;
+    }
+    return XRB_OK;
+}
+
+/* test hook (not part of the reference surface): CUDA's float(acos(double)) table */
+int xrb_match_debug_dist_table(float *out_host, int n) {
+    float *d = nullptr;
+    XRB_CUDA(cudaMalloc(&d, (size_t)n * 4));
+    int rc = launch_dist_table(d, n, nullptr);
+    if (rc == XRB_OK) {
+        cudaError_t e = cudaMemcpy(out_host, d, (size_t)n * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = XRB_ERR_CUDA;
+    }
+    cudaFree(d);
+    return rc;
+}
+
+}  // extern "C"
