@@ -94,22 +94,26 @@ def test_ties_for_best_are_rejected_and_second_counts_equal_values():
 
 def test_tie_break_order_matches_reference_scans_when_ratio_above_one():
     """With ratiomax > 1 a tied best can be accepted; the reported index must follow the
-    reference's scan order: rows prefer the lowest lane (j % 32) then lowest j
-    (ProgramCU.cu:1798-1826); columns prefer the lowest i (:1556-1570,1858-1864)."""
+    reference's scan order: each lane (j % 32) keeps its lowest j, then the 16/8/4/2/1 tree
+    (ProgramCU.cu:1798-1826) prefers the lower tree position, i.e. lanes in bit-reversed
+    order 0,16,8,24,4,20,...; columns prefer the lowest i (:1556-1570,1858-1864)."""
     rng = np.random.default_rng(10)
     pool = synth.random_descriptors(80, rng)
     # query = 0.8 x pool[0]: its dot with pool[0] stays below 2^18, so dist > 0 and a tie
     # (dist == distn) passes dist < distn * 1.5
     d1 = (pool[:1].astype(np.float32) * 0.8).astype(np.uint8)
     d2 = pool[10:80].copy()
-    d2[37] = pool[0]   # lane 5
-    d2[33] = pool[0]   # lane 1  <- wins (lower lane), although 33 < 37 as well
-    d2[64] = pool[0]   # lane 0  <- wins over both (lane 0)
+    d2[2] = pool[0]    # lane 2  (bit-reversed rank 8)
+    d2[52] = pool[0]   # lane 20 (bit-reversed rank 5)  <- beats lane 2 although 52 > 2
+    d2[64] = pool[0]   # lane 0  (rank 0)               <- beats both
     _, m12, _ = ol.match_pair(d1, d2, distmax=1.0, ratiomax=1.5, mbm=0, want_m=True)
     assert m12[0] == 64
     d2[64] = pool[20]
     _, m12, _ = ol.match_pair(d1, d2, distmax=1.0, ratiomax=1.5, mbm=0, want_m=True)
-    assert m12[0] == 33
+    assert m12[0] == 52
+    d2[20] = pool[0]   # same lane 20, lower j wins inside the lane
+    _, m12, _ = ol.match_pair(d1, d2, distmax=1.0, ratiomax=1.5, mbm=0, want_m=True)
+    assert m12[0] == 20
     # columns: lowest row index among ties
     e1 = pool[10:40].copy()
     e1[17] = pool[0]

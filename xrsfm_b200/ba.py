@@ -1,0 +1,186 @@
+"""Host mirror of the reference's bundle-adjustment surface (path B).
+
+``BASolver`` keeps the names and option sets of ``xrsfm::BASolver``
+(src/optimization/ba_solver.h:14-30):
+
+* ``GBA(problem, accurate=True, fix_all_frames=False)``  — ba_solver.cc:594-638
+* ``KGBA(problem)``                                      — ba_solver.cc:640-678 (solver part)
+* ``LBA``-style problems are expressed through ``pt_fixed`` / ``cam_t_fixed`` masks
+  (ba_solver.cc:358-391, 552-584) and ``solve(..., max_iterations=5, ...)``.
+
+The reference mutates an AoS ``Map``; here the problem is the flat SoA the C ABI takes
+(``xrb_ba_problem``, SURVEY.md Appendix B describes the Map -> SoA flattening a C++ shim
+performs — see xrsfm_b200/shim/ba_solver_b200.h).  All arithmetic runs in
+``libxrsfm_b200.so``; numpy arrays are host buffers only.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+# option sets: ba_solver.cc:626-634 and :667-670 on top of InitSolverOptions (:70-77)
+GBA_ACCURATE = dict(max_iterations=50, function_tolerance=1e-5, parameter_tolerance=1e-6)
+GBA_FAST = dict(max_iterations=20, function_tolerance=1e-4, parameter_tolerance=1e-5)
+KGBA_OPTIONS = dict(max_iterations=20, function_tolerance=1e-4, parameter_tolerance=1e-5,
+                    initial_radius=1e6)
+LBA_OPTIONS = dict(max_iterations=5, function_tolerance=1e-4, parameter_tolerance=1e-5)  # :586-590
+
+TERMINATION = {0: "Convergence", 1: "No convergence", 2: "Failure"}  # ba_solver.cc:44-65
+
+_FIELDS = ("cam_q", "cam_t", "pts", "intr", "intr_model", "cam_intr", "obs_cam", "obs_pt",
+           "obs_uv", "cam_q_fixed", "cam_t_fixed", "pt_fixed")
+_DTYPES = dict(cam_q=np.float64, cam_t=np.float64, pts=np.float64, intr=np.float64,
+               intr_model=np.int32, cam_intr=np.int32, obs_cam=np.int32, obs_pt=np.int32,
+               obs_uv=np.float64, cam_q_fixed=np.uint8, cam_t_fixed=np.uint8, pt_fixed=np.uint8)
+
+
+def make_options(**kw):
+    o = _lib.BAOptions()
+    _lib.lib().xrb_ba_default_options(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise TypeError(f"unknown BA option {k!r}")
+        setattr(o, k, v)
+    return o
+
+
+def make_problem(scene):
+    """xrb_ba_problem aliasing the arrays of `scene` (mapping with the xrb_ba_problem field
+    names; arrays must be C-contiguous with the documented dtypes — they are updated in place)."""
+    p = _lib.BAProblem()
+    p.n_cams, p.n_pts = int(scene["n_cams"]), int(scene["n_pts"])
+    p.n_obs, p.n_intr = int(scene["n_obs"]), int(scene["n_intr"])
+    for name in _FIELDS:
+        a = scene[name]
+        if a is None:
+            setattr(p, name, None)
+            continue
+        if not (isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"] and a.dtype == _DTYPES[name]):
+            raise TypeError(f"{name}: need a C-contiguous {np.dtype(_DTYPES[name]).name} array")
+        setattr(p, name, a.ctypes.data)
+    return p
+
+
+def print_solver_summary(s):
+    """PrintSolverSummary (ba_solver.cc:14-68), same fields and layout."""
+    n = max(s.num_residuals_reduced, 1)
+    print(f"{'Residuals : ':>16}{s.num_residuals_reduced}")
+    print(f"{'Parameters : ':>16}{s.num_effective_parameters_reduced}")
+    print(f"{'Iterations : ':>16}{s.num_successful_steps + s.num_unsuccessful_steps}")
+    print(f"{'Time : ':>16}{s.total_time_in_seconds:g} [s]")
+    print(f"{'Initial cost : ':>16}{np.sqrt(s.initial_cost / n):.6g} [px]")
+    print(f"{'Final cost : ':>16}{np.sqrt(s.final_cost / n):.6g} [px]")
+    print(f"{'Termination : ':>16}{TERMINATION.get(s.termination_type, 'Unknown')}\n")
+
+
+class BASolver:
+    """B200 engine behind the reference's BASolver call surface."""
+
+    def __init__(self, device=0):
+        self._device = device
+        self._h = None
+        self._hook = None  # keep the ctypes callback alive
+
+    # -- reference-named entry points -----------------------------------------------------
+    def GBA(self, scene, accurate=True, fix_all_frames=False, verbose=False):
+        """ba_solver.cc:594-638. Gauge: translations of the first two cameras are expected
+        fixed in scene['cam_t_fixed'] (init_id1/init_id2, :611-614); fix_all_frames freezes
+        every pose (:616-621)."""
+        sc = scene
+        if fix_all_frames:
+            sc = dict(scene)
+            sc["cam_q_fixed"] = np.ones(scene["n_cams"], dtype=np.uint8)
+            sc["cam_t_fixed"] = np.ones(scene["n_cams"], dtype=np.uint8)
+        s = self.solve_scene(sc, **(GBA_ACCURATE if accurate else GBA_FAST))
+        if verbose:
+            print_solver_summary(s)
+        return s
+
+    def KGBA(self, scene, verbose=False):
+        """Solver part of ba_solver.cc:640-678 (key-frame selection and UpdateByRefFrame stay
+        with the caller, which passes only key-frames as cameras)."""
+        s = self.solve_scene(scene, **KGBA_OPTIONS)
+        if verbose:
+            print_solver_summary(s)
+        return s
+
+    def LBA(self, scene, verbose=False):
+        """Local BA option set (ba_solver.cc:586-591); the caller supplies the local window and
+        the constant-point / constant-translation masks (:380-382, :552-584)."""
+        s = self.solve_scene(scene, **LBA_OPTIONS)
+        if verbose:
+            print_solver_summary(s)
+        return s
+
+    # -- flat interface ------------------------------------------------------------------
+    def solve_scene(self, scene, **opts):
+        self._ensure()
+        p = make_problem(scene)
+        o = make_options(**opts)
+        s = _lib.BASummary()
+        _lib.check(_lib.lib().xrb_ba_solve(self._h, C.byref(p), C.byref(o), C.byref(s)), "xrb_ba_solve")
+        return s
+
+    def load(self, scene):
+        self._ensure()
+        self._problem = make_problem(scene)
+        self._scene = scene
+        _lib.check(_lib.lib().xrb_ba_load(self._h, C.byref(self._problem)), "xrb_ba_load")
+
+    def reset(self):
+        _lib.check(_lib.lib().xrb_ba_reset(self._h), "xrb_ba_reset")
+
+    def run(self, stream=None, **opts):
+        o = make_options(**opts)
+        s = _lib.BASummary()
+        _lib.check(_lib.lib().xrb_ba_run(self._h, C.byref(o), C.byref(s), stream), "xrb_ba_run")
+        return s
+
+    def fetch(self):
+        _lib.check(_lib.lib().xrb_ba_fetch(self._h, C.byref(self._problem)), "xrb_ba_fetch")
+
+    def residuals(self):
+        out = np.zeros((self._problem.n_obs, 2))
+        _lib.check(_lib.lib().xrb_ba_residuals(self._h, out.ctypes.data), "xrb_ba_residuals")
+        return out
+
+    def profile(self):
+        ms = (C.c_double * 6)()
+        ln = (C.c_int64 * 6)()
+        _lib.check(_lib.lib().xrb_ba_profile(self._h, ms, ln), "xrb_ba_profile")
+        names = ("schur", "solve", "backsub", "cost", "exchange", "run")
+        return {n: (ms[i], ln[i]) for i, n in enumerate(names)}
+
+    def set_exchange(self, rank, world, allreduce):
+        """allreduce(ptr: int, count: int) -> None: in-place SUM over ranks of `count` doubles
+        at device address `ptr` (see include/xrsfm_b200.h xrb_ba_set_exchange)."""
+        self._ensure()
+
+        def _cb(buf, count, _user):
+            try:
+                allreduce(int(buf), int(count))
+                return 0
+            except Exception as e:  # noqa: BLE001 - surfaced as XRB_ERR_COMM
+                print("exchange hook failed:", e)
+                return 1
+
+        self._hook = _lib.ALLREDUCE_FN(_cb)
+        _lib.check(_lib.lib().xrb_ba_set_exchange(self._h, rank, world, self._hook, None),
+                   "xrb_ba_set_exchange")
+
+    # -- plumbing ------------------------------------------------------------------------
+    def _ensure(self):
+        if self._h is None:
+            h = _lib.lib().xrb_ba_create(self._device)
+            if not h:
+                raise _lib.XrbError("xrb_ba_create failed: " + _lib.last_error())
+            self._h = h
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _lib.lib().xrb_ba_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

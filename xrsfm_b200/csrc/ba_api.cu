@@ -1,33 +1,642 @@
-// ba_api.cu — C ABI of path B (placeholder while the kernels land).
-#include "common.cuh"
+// ba_api.cu — C ABI of path B and the host-side Levenberg–Marquardt controller.
+//
+// The controller restates ceres::TrustRegionMinimizer + LevenbergMarquardtStrategy for the
+// options BASolver selects (ba_solver.cc:70-77,624-634,665-670); all arithmetic over
+// observations, points and the reduced camera system runs in the kernels of
+// ba_kernels.cu / ba_chol.cu.  One device->host read of a few scalars per LM iteration is
+// the only synchronisation.  Multi-GPU: points are sharded, cameras replicated, one SUM
+// all-reduce of the packed reduced system per linear solve (xrb_ba_set_exchange).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "ba_kernels.cuh"
 
 using namespace xrb;
 
+namespace {
+
+struct Ev {
+    cudaEvent_t e = nullptr;
+    void rec(cudaStream_t s) {
+        if (!e) cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+    }
+};
+
+}  // namespace
+
+struct xrb_ba_solver {
+    int device = 0;
+    int rank = 0, world = 1;
+    xrb_allreduce_fn fn = nullptr;
+    void *user = nullptr;
+    cudaStream_t own_stream = nullptr;
+
+    bool loaded = false;
+    int C = 0, P_total = 0, O_total = 0, n_intr = 0;
+    int P_local = 0, O_local = 0, p_lo = 0;
+    int nc = 0, ld = 0, bw = 0;
+    int n_var_q = 0, n_var_t = 0, n_var_pts = 0, n_res_blocks = 0;
+    std::vector<int32_t> obs_orig_host;
+
+    // device: problem
+    DevBuf d_intr, d_intr_model, d_cam_intr, d_colq, d_colt, d_pt_ptr, d_obs_cam, d_obs_uv,
+        d_pt_var, d_obs_orig;
+    // device: states
+    DevBuf d_q[3], d_t[3], d_X[3];  // 0 = current, 1 = candidate, 2 = initial copy
+    int cur = 0;
+    // device: linear system.  E = [S | U | gc | n2c | scalE(8) | slots(world)]
+    DevBuf d_E, d_Vinv, d_gp, d_sc, d_sp, d_linv, d_yc, d_step_p, d_scal, d_full;
+    size_t off_U = 0, off_gc = 0, off_n2c = 0, off_scalE = 0, off_slots = 0, E_count = 0;
+    double *h_scal = nullptr;  // pinned mirror: [scalE(8) | slots(world) | scal2(8) | scalL(8)]
+
+    double ms[6] = {0, 0, 0, 0, 0, 0};
+    int64_t launches[6] = {0, 0, 0, 0, 0, 0};
+
+    BAProblemDev prob() const {
+        BAProblemDev p;
+        p.n_cams = C, p.n_pts_local = P_local, p.n_obs_local = O_local, p.nc = nc;
+        p.intr = d_intr.as<double>(), p.intr_model = d_intr_model.as<int32_t>();
+        p.cam_intr = d_cam_intr.as<int32_t>();
+        p.colq = d_colq.as<int32_t>(), p.colt = d_colt.as<int32_t>();
+        p.pt_ptr = d_pt_ptr.as<int32_t>(), p.obs_cam = d_obs_cam.as<int32_t>();
+        p.obs_uv = d_obs_uv.as<double>(), p.pt_var = d_pt_var.as<uint8_t>();
+        return p;
+    }
+    BAStateDev state(int i) const { return {d_q[i].as<double>(), d_t[i].as<double>(), d_X[i].as<double>()}; }
+    BALinSys linsys() const {
+        BALinSys L;
+        double *E = d_E.as<double>();
+        L.S = E, L.ld = ld, L.U = E + off_U, L.gc = E + off_gc, L.n2c = E + off_n2c;
+        L.Vinv = d_Vinv.as<double>(), L.gp = d_gp.as<double>();
+        L.sc = d_sc.as<double>(), L.sp = d_sp.as<double>();
+        return L;
+    }
+    double *scalE() const { return d_E.as<double>() + off_scalE; }
+    double *slots() const { return d_E.as<double>() + off_slots; }
+    double *scal2() const { return d_scal.as<double>(); }
+    double *scalL() const { return d_scal.as<double>() + SC_COUNT; }
+
+    int exchange(double *buf, size_t count, cudaStream_t st) {
+        if (world <= 1) return XRB_OK;
+        if (!fn) {
+            set_error("world > 1 but no exchange hook set");
+            return XRB_ERR_COMM;
+        }
+        // the hook enqueues on ITS stream; order it after ours and ours after it
+        XRB_CUDA(cudaStreamSynchronize(st));
+        if (fn(buf, count, user) != 0) {
+            set_error("exchange hook failed");
+            return XRB_ERR_COMM;
+        }
+        launches[4]++;
+        return XRB_OK;
+    }
+};
+
+namespace {
+
+template <class T>
+int upload(DevBuf &b, const T *src, size_t n, cudaStream_t st) {
+    int rc = b.reserve(std::max<size_t>(n, 1) * sizeof(T));
+    if (rc) return rc;
+    if (n) XRB_CUDA(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    return XRB_OK;
+}
+
+int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
+    XRB_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = s->own_stream;
+    if (!P || P->n_cams < 0 || P->n_pts < 0 || P->n_obs < 0 || P->n_intr <= 0 || !P->cam_q || !P->cam_t ||
+        !P->pts || !P->intr || !P->intr_model || !P->cam_intr || (P->n_obs && (!P->obs_cam || !P->obs_pt || !P->obs_uv))) {
+        set_error("ba_load: null or negative field in xrb_ba_problem");
+        return XRB_ERR_INVALID;
+    }
+    const int C = P->n_cams, NP = P->n_pts, NO = P->n_obs;
+    for (int o = 0; o < NO; ++o)
+        if (P->obs_cam[o] < 0 || P->obs_cam[o] >= C || P->obs_pt[o] < 0 || P->obs_pt[o] >= NP) {
+            set_error("ba_load: observation %d references camera %d / point %d out of range", o, P->obs_cam[o], P->obs_pt[o]);
+            return XRB_ERR_INVALID;
+        }
+    for (int c = 0; c < C; ++c)
+        if (P->cam_intr[c] < 0 || P->cam_intr[c] >= P->n_intr) {
+            set_error("ba_load: camera %d references intrinsics %d out of range", c, P->cam_intr[c]);
+            return XRB_ERR_INVALID;
+        }
+    for (int i = 0; i < P->n_intr; ++i)
+        if (P->intr_model[i] < 0 || P->intr_model[i] > 4) {
+            set_error("ba_load: unknown camera model id %d (camera_model.hpp defines 0..4)", P->intr_model[i]);
+            return XRB_ERR_INVALID;
+        }
+    s->C = C, s->P_total = NP, s->O_total = NO, s->n_intr = P->n_intr;
+
+    // ---- global structure: CSR by point (stable), variable blocks, reduced columns
+    std::vector<int> pt_ptr(NP + 1, 0), cam_obs(C, 0);
+    for (int o = 0; o < NO; ++o) pt_ptr[P->obs_pt[o] + 1]++, cam_obs[P->obs_cam[o]]++;
+    for (int p = 0; p < NP; ++p) pt_ptr[p + 1] += pt_ptr[p];
+    std::vector<int> pt_obs(NO);
+    {
+        std::vector<int> cursor(pt_ptr.begin(), pt_ptr.end() - 1);
+        for (int o = 0; o < NO; ++o) pt_obs[cursor[P->obs_pt[o]]++] = o;
+    }
+    std::vector<int32_t> colq(C, -1), colt(C, -1);
+    s->nc = 0, s->n_var_q = s->n_var_t = 0;
+    for (int c = 0; c < C; ++c) {
+        if (!cam_obs[c]) continue;  // not in the ceres::Problem at all
+        if (!(P->cam_q_fixed && P->cam_q_fixed[c])) colq[c] = s->nc, s->nc += 3, s->n_var_q++;
+        if (!(P->cam_t_fixed && P->cam_t_fixed[c])) colt[c] = s->nc, s->nc += 3, s->n_var_t++;
+    }
+    std::vector<uint8_t> pt_var(NP, 0);
+    s->n_var_pts = 0;
+    for (int p = 0; p < NP; ++p)
+        if (pt_ptr[p + 1] > pt_ptr[p] && !(P->pt_fixed && P->pt_fixed[p])) pt_var[p] = 1, s->n_var_pts++;
+    s->n_res_blocks = 0;
+    for (int o = 0; o < NO; ++o) {
+        const int c = P->obs_cam[o];
+        s->n_res_blocks += (colq[c] >= 0 || colt[c] >= 0 || pt_var[P->obs_pt[o]]) ? 1 : 0;
+    }
+    // half bandwidth of S in scalars
+    int bw = 0;
+    for (int p = 0; p < NP; ++p) {
+        if (!pt_var[p]) continue;
+        int lo = INT32_MAX, hi = -1;
+        for (int k = pt_ptr[p]; k < pt_ptr[p + 1]; ++k) {
+            const int c = P->obs_cam[pt_obs[k]];
+            if (colq[c] >= 0) lo = std::min(lo, colq[c]), hi = std::max(hi, colq[c] + 2);
+            if (colt[c] >= 0) lo = std::min(lo, colt[c]), hi = std::max(hi, colt[c] + 2);
+        }
+        if (hi >= 0) bw = std::max(bw, hi - lo);
+    }
+    s->bw = std::max(bw, 5);
+
+    // ---- shard the points over ranks, balanced by the Schur work sum k_p^2 + k_p
+    int p_lo = 0, p_hi = NP;
+    if (s->world > 1) {
+        std::vector<double> w(NP + 1, 0.0);
+        for (int p = 0; p < NP; ++p) {
+            const double k = pt_ptr[p + 1] - pt_ptr[p];
+            w[p + 1] = w[p] + k * k + 4.0 * k;
+        }
+        auto cut = [&](int r) {
+            const double target = w[NP] * r / s->world;
+            return (int)(std::lower_bound(w.begin(), w.end(), target) - w.begin());
+        };
+        p_lo = std::min(NP, cut(s->rank)), p_hi = s->rank + 1 == s->world ? NP : std::min(NP, cut(s->rank + 1));
+        if (s->rank == 0) p_lo = 0;
+        p_hi = std::max(p_hi, p_lo);
+    }
+    s->p_lo = p_lo, s->P_local = p_hi - p_lo;
+    const int o_lo = pt_ptr[p_lo], o_hi = pt_ptr[p_hi];
+    s->O_local = o_hi - o_lo;
+    std::vector<int32_t> l_ptr(s->P_local + 1), l_cam(s->O_local), l_orig(s->O_local);
+    std::vector<double> l_uv(2 * (size_t)s->O_local);
+    for (int p = 0; p <= s->P_local; ++p) l_ptr[p] = pt_ptr[p_lo + p] - o_lo;
+    for (int k = 0; k < s->O_local; ++k) {
+        const int o = pt_obs[o_lo + k];
+        l_cam[k] = P->obs_cam[o], l_orig[k] = o;
+        l_uv[2 * (size_t)k] = P->obs_uv[2 * (size_t)o], l_uv[2 * (size_t)k + 1] = P->obs_uv[2 * (size_t)o + 1];
+    }
+    s->obs_orig_host = l_orig;
+
+    int rc;
+    if ((rc = upload(s->d_intr, P->intr, 8 * (size_t)P->n_intr, st))) return rc;
+    if ((rc = upload(s->d_intr_model, P->intr_model, (size_t)P->n_intr, st))) return rc;
+    if ((rc = upload(s->d_cam_intr, P->cam_intr, (size_t)C, st))) return rc;
+    if ((rc = upload(s->d_colq, colq.data(), (size_t)C, st))) return rc;
+    if ((rc = upload(s->d_colt, colt.data(), (size_t)C, st))) return rc;
+    if ((rc = upload(s->d_pt_ptr, l_ptr.data(), l_ptr.size(), st))) return rc;
+    if ((rc = upload(s->d_obs_cam, l_cam.data(), l_cam.size(), st))) return rc;
+    if ((rc = upload(s->d_obs_orig, l_orig.data(), l_orig.size(), st))) return rc;
+    if ((rc = upload(s->d_obs_uv, l_uv.data(), l_uv.size(), st))) return rc;
+    if ((rc = upload(s->d_pt_var, pt_var.data() + p_lo, (size_t)s->P_local, st))) return rc;
+    for (int i = 0; i < 3; ++i) {
+        if ((rc = upload(s->d_q[i], P->cam_q, 4 * (size_t)C, st))) return rc;
+        if ((rc = upload(s->d_t[i], P->cam_t, 3 * (size_t)C, st))) return rc;
+        if ((rc = upload(s->d_X[i], P->pts + 3 * (size_t)p_lo, 3 * (size_t)s->P_local, st))) return rc;
+    }
+    s->cur = 0;
+    // ---- linear-system storage
+    const int nc = s->nc;
+    s->ld = ((nc + 1 + 7) / 8) * 8;
+    const size_t nS = (size_t)(nc + 1) * s->ld;
+    s->off_U = nS, s->off_gc = s->off_U + (size_t)nc * 6, s->off_n2c = s->off_gc + nc;
+    s->off_scalE = s->off_n2c + nc, s->off_slots = s->off_scalE + SC_COUNT;
+    s->E_count = s->off_slots + s->world;
+    if ((rc = s->d_E.reserve(s->E_count * 8))) return rc;
+    if ((rc = s->d_Vinv.reserve(std::max<size_t>(1, 6 * (size_t)s->P_local) * 8))) return rc;
+    if ((rc = s->d_gp.reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
+    if ((rc = s->d_sp.reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
+    if ((rc = s->d_step_p.reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
+    if ((rc = s->d_sc.reserve(std::max<size_t>(1, nc) * 8))) return rc;
+    if ((rc = s->d_yc.reserve(std::max<size_t>(1, nc) * 8))) return rc;
+    if ((rc = s->d_linv.reserve((size_t)((nc + 63) / 64 + 1) * 64 * 64 * 8))) return rc;
+    if ((rc = s->d_scal.reserve(2 * SC_COUNT * 8))) return rc;
+    if (!s->h_scal) XRB_CUDA(cudaMallocHost(&s->h_scal, (3 * SC_COUNT + 64) * sizeof(double)));
+    if (s->world > 64) {
+        set_error("world %d > 64 not supported", s->world);
+        return XRB_ERR_INVALID;
+    }
+    XRB_CUDA(cudaStreamSynchronize(st));
+    s->loaded = true;
+    return XRB_OK;
+}
+
+struct StepOut {
+    double model_cost_change, cand_cost, step_norm, cand_xnorm, grad_max;
+    bool ok;
+};
+
+// One linear solve + candidate evaluation from the state in slot `cur`; candidate in slot 1-cur.
+int compute_step(xrb_ba_solver *s, const BAConsts &k, double radius, cudaStream_t st, StepOut &out,
+                 Ev ev[8]) {
+    const BAProblemDev P = s->prob();
+    const BALinSys L = s->linsys();
+    const BAStateDev x = s->state(s->cur), cand = s->state(1 - s->cur);
+    const double inv_radius = 1.0 / radius;
+    int rc;
+    ev[0].rec(st);
+    // zero S, U, gc (n2c untouched), scalE + slots, scal2 + scalL
+    XRB_CUDA(cudaMemsetAsync(s->d_E.p, 0, s->off_n2c * 8, st));
+    XRB_CUDA(cudaMemsetAsync(s->scalE(), 0, (SC_COUNT + s->world) * 8, st));
+    XRB_CUDA(cudaMemsetAsync(s->d_scal.p, 0, 2 * SC_COUNT * 8, st));
+    if ((rc = ba_launch_schur(P, x, k, L, inv_radius, s->scalE(), st))) return rc;
+    s->launches[0]++;
+    ev[1].rec(st);
+    if (s->world > 1) {
+        XRB_CUDA(cudaMemcpyAsync(s->slots() + s->rank, s->scalE() + SC_GRAD_MAX_PT, 8, cudaMemcpyDeviceToDevice, st));
+        // S | U | gc  and the scalar tail travel in two pieces (n2c is skipped)
+        if ((rc = s->exchange(s->d_E.as<double>(), s->off_n2c, st))) return rc;
+        if ((rc = s->exchange(s->scalE(), SC_COUNT + s->world, st))) return rc;
+    }
+    ev[2].rec(st);
+    if ((rc = ba_launch_cam_diag(P, x, L, inv_radius, s->scalL(), st))) return rc;
+    if ((rc = ba_launch_cholesky_solve(L.S, s->nc, s->ld, s->bw, s->d_linv.as<double>(), s->d_yc.as<double>(),
+                                       s->scalL() + SC_FAIL, st, &s->launches[1])))
+        return rc;
+    s->launches[1]++;
+    ev[3].rec(st);
+    if ((rc = ba_launch_backsub(P, x, cand, k, L, s->d_yc.as<double>(), s->d_step_p.as<double>(), s->scal2(), st))) return rc;
+    if ((rc = ba_launch_cam_update(P, x, cand, L, s->d_yc.as<double>(), s->scal2(), s->rank == 0, st))) return rc;
+    s->launches[2] += 2;
+    ev[4].rec(st);
+    if ((rc = ba_launch_cost(P, cand, k, 0, s->scal2() + SC_CAND_COST, st))) return rc;
+    s->launches[3]++;
+    ev[5].rec(st);
+    if ((rc = s->exchange(s->scal2(), SC_COUNT, st))) return rc;
+    ev[6].rec(st);
+    double *h = s->h_scal;
+    XRB_CUDA(cudaMemcpyAsync(h, s->scalE(), (SC_COUNT + s->world) * 8, cudaMemcpyDeviceToHost, st));
+    XRB_CUDA(cudaMemcpyAsync(h + SC_COUNT + 64, s->d_scal.p, 2 * SC_COUNT * 8, cudaMemcpyDeviceToHost, st));
+    XRB_CUDA(cudaStreamSynchronize(st));
+    const double *hE = h, *hslots = h + SC_COUNT, *h2 = h + SC_COUNT + 64, *hL = h2 + SC_COUNT;
+    double gpt = 0.0;
+    if (s->world > 1)
+        for (int r = 0; r < s->world; ++r) gpt = std::max(gpt, hslots[r]);
+    else
+        gpt = hE[SC_GRAD_MAX_PT];
+    out.grad_max = std::max(gpt, hL[SC_GRAD_MAX_CAM]);
+    out.model_cost_change = h2[SC_MODEL_CHANGE];
+    out.cand_cost = h2[SC_CAND_COST];
+    out.step_norm = std::sqrt(h2[SC_STEP_NORM2]);
+    out.cand_xnorm = std::sqrt(h2[SC_XNORM2]);
+    out.ok = hE[SC_FAIL] == 0.0 && h2[SC_FAIL] == 0.0 && hL[SC_FAIL] == 0.0 && std::isfinite(out.model_cost_change) &&
+             std::isfinite(out.cand_cost) && std::isfinite(out.step_norm);
+    // phase timings
+    static const int phase_of[6] = {0, 4, 1, 2, 3, 4};
+    for (int i = 0; i < 6; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ev[i].e, ev[i + 1].e) == cudaSuccess) s->ms[phase_of[i]] += t;
+    }
+    return XRB_OK;
+}
+
+int reduce_scalar_cost(xrb_ba_solver *s, const BAConsts &k, int state_slot, int mode, cudaStream_t st, double &cost) {
+    XRB_CUDA(cudaMemsetAsync(s->d_scal.p, 0, 2 * SC_COUNT * 8, st));
+    int rc = ba_launch_cost(s->prob(), s->state(state_slot), k, mode, s->scal2() + SC_COST, st);
+    if (rc) return rc;
+    s->launches[3]++;
+    if ((rc = s->exchange(s->scal2(), SC_COUNT, st))) return rc;
+    XRB_CUDA(cudaMemcpyAsync(s->h_scal, s->scal2(), SC_COUNT * 8, cudaMemcpyDeviceToHost, st));
+    XRB_CUDA(cudaStreamSynchronize(st));
+    cost = s->h_scal[SC_COST];
+    return XRB_OK;
+}
+
+int do_run(xrb_ba_solver *s, const xrb_ba_options *O, xrb_ba_summary *sum, cudaStream_t st) {
+    if (!s->loaded) {
+        set_error("ba_run: no problem loaded");
+        return XRB_ERR_INVALID;
+    }
+    XRB_CUDA(cudaSetDevice(s->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    memset(sum, 0, sizeof *sum);
+    for (int i = 0; i < 6; ++i) s->ms[i] = 0.0, s->launches[i] = 0;
+    BAConsts k{O->huber_a, O->huber_a * O->huber_a, O->min_depth, O->neg_depth_residual};
+    sum->num_residuals_reduced = 2 * s->n_res_blocks;
+    sum->num_effective_parameters_reduced = 3 * (s->n_var_q + s->n_var_t + s->n_var_pts);
+    sum->termination_type = XRB_BA_NO_CONVERGENCE;
+    Ev ev[8], ev_run[2];
+    ev_run[0].rec(st);
+    int rc;
+    double fixed_cost = 0.0, x_cost = 0.0;
+    if ((rc = reduce_scalar_cost(s, k, s->cur, 1, st, fixed_cost))) return rc;
+    sum->fixed_cost = fixed_cost;
+    if (s->n_res_blocks == 0 || sum->num_effective_parameters_reduced == 0) {
+        sum->initial_cost = sum->final_cost = fixed_cost;
+        sum->termination_type = XRB_BA_CONVERGENCE;
+        return XRB_OK;
+    }
+    if ((rc = reduce_scalar_cost(s, k, s->cur, 0, st, x_cost))) return rc;
+    // ---- Jacobi scaling from the iteration-0 Jacobian
+    {
+        const BALinSys L = s->linsys();
+        const size_t npl = 3 * (size_t)s->P_local;
+        std::vector<double> ones(std::max<size_t>(npl, (size_t)s->nc), 1.0);
+        if (npl) XRB_CUDA(cudaMemcpyAsync(L.sp, ones.data(), npl * 8, cudaMemcpyHostToDevice, st));
+        if (s->nc) XRB_CUDA(cudaMemcpyAsync(L.sc, ones.data(), (size_t)s->nc * 8, cudaMemcpyHostToDevice, st));
+        XRB_CUDA(cudaMemsetAsync(L.n2c, 0, std::max<size_t>(1, s->nc) * 8, st));
+        XRB_CUDA(cudaStreamSynchronize(st));  // `ones` is pageable
+        if ((rc = ba_launch_colnorm(s->prob(), s->state(s->cur), k, L, st))) return rc;
+        if ((rc = s->exchange(L.n2c, (size_t)s->nc, st))) return rc;
+        if ((rc = ba_launch_finish_scaling(s->prob(), L, st))) return rc;
+        s->launches[0] += 2;
+    }
+    // ||x|| over the variable blocks of the start point
+    double xnorm;
+    {
+        std::vector<double> hq(4 * (size_t)s->C), ht(3 * (size_t)s->C), hX(3 * (size_t)s->P_local);
+        std::vector<int32_t> colq(s->C), colt(s->C);
+        std::vector<uint8_t> pv(s->P_local);
+        XRB_CUDA(cudaMemcpyAsync(hq.data(), s->d_q[s->cur].p, hq.size() * 8, cudaMemcpyDeviceToHost, st));
+        XRB_CUDA(cudaMemcpyAsync(ht.data(), s->d_t[s->cur].p, ht.size() * 8, cudaMemcpyDeviceToHost, st));
+        if (s->P_local) XRB_CUDA(cudaMemcpyAsync(hX.data(), s->d_X[s->cur].p, hX.size() * 8, cudaMemcpyDeviceToHost, st));
+        XRB_CUDA(cudaMemcpyAsync(colq.data(), s->d_colq.p, colq.size() * 4, cudaMemcpyDeviceToHost, st));
+        XRB_CUDA(cudaMemcpyAsync(colt.data(), s->d_colt.p, colt.size() * 4, cudaMemcpyDeviceToHost, st));
+        if (s->P_local) XRB_CUDA(cudaMemcpyAsync(pv.data(), s->d_pt_var.p, pv.size(), cudaMemcpyDeviceToHost, st));
+        XRB_CUDA(cudaStreamSynchronize(st));
+        double n2 = 0.0;
+        if (s->rank == 0)
+            for (int c = 0; c < s->C; ++c) {
+                if (colq[c] >= 0) for (int j = 0; j < 4; ++j) n2 += hq[4 * c + j] * hq[4 * c + j];
+                if (colt[c] >= 0) for (int j = 0; j < 3; ++j) n2 += ht[3 * c + j] * ht[3 * c + j];
+            }
+        for (int p = 0; p < s->P_local; ++p)
+            if (pv[p]) for (int j = 0; j < 3; ++j) n2 += hX[3 * (size_t)p + j] * hX[3 * (size_t)p + j];
+        if (s->world > 1) {
+            XRB_CUDA(cudaMemsetAsync(s->d_scal.p, 0, 2 * SC_COUNT * 8, st));
+            XRB_CUDA(cudaMemcpyAsync(s->scal2() + SC_XNORM2, &n2, 8, cudaMemcpyHostToDevice, st));
+            if ((rc = s->exchange(s->scal2(), SC_COUNT, st))) return rc;
+            XRB_CUDA(cudaMemcpyAsync(&n2, s->scal2() + SC_XNORM2, 8, cudaMemcpyDeviceToHost, st));
+            XRB_CUDA(cudaStreamSynchronize(st));
+        }
+        xnorm = std::sqrt(n2);
+    }
+
+    auto log_iter = [&](const xrb_ba_iteration &it) {
+        if (sum->n_iterations_logged < 128) sum->iterations[sum->n_iterations_logged++] = it;
+        if (it.step_is_successful) sum->num_successful_steps++; else sum->num_unsuccessful_steps++;
+        if (O->verbose && s->rank == 0)
+            printf("%4d % .6e % .2e % .2e % .2e % .2e % .2e\n", it.iteration, it.cost, it.cost_change,
+                   it.gradient_max_norm, it.step_norm, it.relative_decrease, it.trust_region_radius);
+    };
+
+    double radius = O->initial_radius, decrease_factor = 2.0;
+    xrb_ba_iteration it;
+    memset(&it, 0, sizeof it);
+    it.iteration = 0, it.step_is_valid = 1, it.step_is_successful = 1;
+    it.cost = x_cost + fixed_cost, it.trust_region_radius = radius;
+    sum->initial_cost = it.cost;
+    StepOut so;
+    if ((rc = compute_step(s, k, radius, st, so, ev))) return rc;
+    bool have_step = true;
+    it.gradient_max_norm = so.grad_max;
+    log_iter(it);
+    int iteration = 0, consecutive_invalid = 0;
+    for (;;) {
+        // FinalizeIterationAndCheckIfMinimizerCanContinue
+        if (iteration >= O->max_iterations) { sum->termination_type = XRB_BA_NO_CONVERGENCE; break; }
+        if (!O->fixed_iterations && it.gradient_max_norm <= O->gradient_tolerance) { sum->termination_type = XRB_BA_CONVERGENCE; break; }
+        if (radius <= 1e-32) { sum->termination_type = XRB_BA_CONVERGENCE; break; }
+        iteration++;
+        xrb_ba_iteration cur;
+        memset(&cur, 0, sizeof cur);
+        cur.iteration = iteration;
+        if (!have_step && (rc = compute_step(s, k, radius, st, so, ev))) return rc;
+        have_step = false;
+        sum->num_lm_iterations++;
+        cur.model_cost_change = so.model_cost_change;
+        cur.step_is_valid = so.ok && so.model_cost_change > 0.0;
+        if (!cur.step_is_valid) {  // HandleInvalidStep
+            if (++consecutive_invalid >= 5) { sum->termination_type = XRB_BA_FAILURE; break; }
+            radius *= 0.5;
+            cur.cost = x_cost + fixed_cost;
+            cur.gradient_max_norm = it.gradient_max_norm;
+            cur.trust_region_radius = radius;
+            it = cur;
+            log_iter(it);
+            continue;
+        }
+        consecutive_invalid = 0;
+        cur.step_norm = so.step_norm;
+        // ParameterToleranceReached, then FunctionToleranceReached — before accept/reject
+        if (!O->fixed_iterations && cur.step_norm <= O->parameter_tolerance * (xnorm + O->parameter_tolerance)) {
+            sum->termination_type = XRB_BA_CONVERGENCE;
+            break;
+        }
+        cur.cost_change = x_cost - so.cand_cost;
+        if (!O->fixed_iterations && std::fabs(cur.cost_change) <= O->function_tolerance * x_cost) {
+            sum->termination_type = XRB_BA_CONVERGENCE;
+            break;
+        }
+        cur.relative_decrease = cur.cost_change / so.model_cost_change;
+        const double cand_cost = so.cand_cost;
+        if (cur.relative_decrease > 1e-3) {  // HandleSuccessfulStep
+            s->cur = 1 - s->cur;
+            xnorm = so.cand_xnorm;
+            x_cost = cand_cost;
+            cur.step_is_successful = 1;
+            radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * cur.relative_decrease - 1.0, 3));
+            radius = std::min(1e16, radius);
+            decrease_factor = 2.0;
+            if ((rc = compute_step(s, k, radius, st, so, ev))) return rc;  // also the gradient at the new point
+            have_step = true;
+            cur.gradient_max_norm = so.grad_max;
+        } else {  // StepRejected
+            radius = radius / decrease_factor;
+            decrease_factor *= 2.0;
+            cur.gradient_max_norm = it.gradient_max_norm;
+        }
+        cur.cost = cand_cost + fixed_cost;
+        cur.trust_region_radius = radius;
+        it = cur;
+        log_iter(it);
+    }
+    sum->final_cost = sum->initial_cost;
+    for (int i = 0; i < sum->n_iterations_logged; ++i) sum->final_cost = std::min(sum->final_cost, sum->iterations[i].cost);
+    ev_run[1].rec(st);
+    XRB_CUDA(cudaStreamSynchronize(st));
+    float tr = 0.f;
+    cudaEventElapsedTime(&tr, ev_run[0].e, ev_run[1].e);
+    s->ms[5] = tr;
+    sum->linear_solver_seconds = (s->ms[0] + s->ms[1] + s->ms[2]) * 1e-3;
+    sum->residual_seconds = s->ms[3] * 1e-3;
+    sum->total_time_in_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (auto &e : ev) if (e.e) cudaEventDestroy(e.e);
+    for (auto &e : ev_run) if (e.e) cudaEventDestroy(e.e);
+    return XRB_OK;
+}
+
+int do_fetch(xrb_ba_solver *s, xrb_ba_problem *P) {
+    if (!s->loaded || !P || P->n_cams != s->C || P->n_pts != s->P_total) {
+        set_error("ba_fetch: problem does not match the loaded one");
+        return XRB_ERR_INVALID;
+    }
+    XRB_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = s->own_stream;
+    XRB_CUDA(cudaMemcpyAsync(P->cam_q, s->d_q[s->cur].p, 4 * (size_t)s->C * 8, cudaMemcpyDeviceToHost, st));
+    XRB_CUDA(cudaMemcpyAsync(P->cam_t, s->d_t[s->cur].p, 3 * (size_t)s->C * 8, cudaMemcpyDeviceToHost, st));
+    if (s->world <= 1) {
+        if (s->P_local)
+            XRB_CUDA(cudaMemcpyAsync(P->pts, s->d_X[s->cur].p, 3 * (size_t)s->P_local * 8, cudaMemcpyDeviceToHost, st));
+    } else {  // every rank returns every point: zero-padded shards summed through the hook
+        int rc = s->d_full.reserve(std::max<size_t>(1, 3 * (size_t)s->P_total) * 8);
+        if (rc) return rc;
+        XRB_CUDA(cudaMemsetAsync(s->d_full.p, 0, 3 * (size_t)s->P_total * 8, st));
+        if (s->P_local)
+            XRB_CUDA(cudaMemcpyAsync(s->d_full.as<double>() + 3 * (size_t)s->p_lo, s->d_X[s->cur].p,
+                                     3 * (size_t)s->P_local * 8, cudaMemcpyDeviceToDevice, st));
+        if ((rc = s->exchange(s->d_full.as<double>(), 3 * (size_t)s->P_total, st))) return rc;
+        XRB_CUDA(cudaMemcpyAsync(P->pts, s->d_full.p, 3 * (size_t)s->P_total * 8, cudaMemcpyDeviceToHost, st));
+    }
+    XRB_CUDA(cudaStreamSynchronize(st));
+    return XRB_OK;
+}
+
+}  // namespace
+
 extern "C" {
+
 void xrb_ba_default_options(xrb_ba_options *o) {
-    o->max_iterations = 50;
+    if (!o) return;
+    o->max_iterations = 50;        // ceres::Solver::Options defaults ...
     o->function_tolerance = 1e-6;
     o->parameter_tolerance = 1e-8;
     o->gradient_tolerance = 1e-10;
     o->initial_radius = 1e4;
-    o->huber_a = 5.99;
-    o->min_depth = 1e-2;
-    o->neg_depth_residual = 12.0;
+    o->huber_a = 5.99;             // ... and the reference's constants: ba_solver.cc:343,
+    o->min_depth = 1e-2;           // cost_factor_ceres.h:29
+    o->neg_depth_residual = 12.0;  // cost_factor_ceres.h:31
     o->verbose = 0;
     o->fixed_iterations = 0;
 }
+
 xrb_ba_solver *xrb_ba_create(int device) {
     if (select_device(device) != XRB_OK) return nullptr;
-    set_error("BA engine not built yet");
-    return nullptr;
+    xrb_ba_solver *s = new xrb_ba_solver();
+    s->device = device;
+    if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        delete s;
+        return nullptr;
+    }
+    return s;
 }
-void xrb_ba_destroy(xrb_ba_solver *) {}
-int xrb_ba_set_exchange(xrb_ba_solver *, int, int, xrb_allreduce_fn, void *) { return XRB_ERR_INVALID; }
-int xrb_ba_solve(xrb_ba_solver *, const xrb_ba_problem *, const xrb_ba_options *, xrb_ba_summary *) { return XRB_ERR_INVALID; }
-int xrb_ba_load(xrb_ba_solver *, const xrb_ba_problem *) { return XRB_ERR_INVALID; }
-int xrb_ba_reset(xrb_ba_solver *) { return XRB_ERR_INVALID; }
-int xrb_ba_run(xrb_ba_solver *, const xrb_ba_options *, xrb_ba_summary *, void *) { return XRB_ERR_INVALID; }
-int xrb_ba_fetch(xrb_ba_solver *, xrb_ba_problem *) { return XRB_ERR_INVALID; }
-int xrb_ba_residuals(xrb_ba_solver *, double *) { return XRB_ERR_INVALID; }
-int xrb_ba_profile(const xrb_ba_solver *, double *, int64_t *) { return XRB_ERR_INVALID; }
+
+void xrb_ba_destroy(xrb_ba_solver *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->own_stream);
+    DevBuf *bufs[] = {&s->d_intr, &s->d_intr_model, &s->d_cam_intr, &s->d_colq, &s->d_colt, &s->d_pt_ptr,
+                      &s->d_obs_cam, &s->d_obs_uv, &s->d_pt_var, &s->d_obs_orig, &s->d_E, &s->d_Vinv, &s->d_gp,
+                      &s->d_sc, &s->d_sp, &s->d_linv, &s->d_yc, &s->d_step_p, &s->d_scal, &s->d_full};
+    for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < 3; ++i) s->d_q[i].release(), s->d_t[i].release(), s->d_X[i].release();
+    if (s->h_scal) cudaFreeHost(s->h_scal);
+    cudaStreamDestroy(s->own_stream);
+    delete s;
 }
+
+int xrb_ba_set_exchange(xrb_ba_solver *s, int rank, int world, xrb_allreduce_fn fn, void *user) {
+    if (!s || world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) {
+        set_error("ba_set_exchange: bad rank/world/hook");
+        return XRB_ERR_INVALID;
+    }
+    s->rank = rank, s->world = world, s->fn = fn, s->user = user;
+    s->loaded = false;  // sharding changes
+    return XRB_OK;
+}
+
+int xrb_ba_load(xrb_ba_solver *s, const xrb_ba_problem *prob) {
+    if (!s) return XRB_ERR_INVALID;
+    return do_load(s, prob);
+}
+
+int xrb_ba_reset(xrb_ba_solver *s) {
+    if (!s || !s->loaded) return XRB_ERR_INVALID;
+    XRB_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = s->own_stream;
+    s->cur = 0;
+    XRB_CUDA(cudaMemcpyAsync(s->d_q[0].p, s->d_q[2].p, 4 * (size_t)s->C * 8, cudaMemcpyDeviceToDevice, st));
+    XRB_CUDA(cudaMemcpyAsync(s->d_t[0].p, s->d_t[2].p, 3 * (size_t)s->C * 8, cudaMemcpyDeviceToDevice, st));
+    if (s->P_local)
+        XRB_CUDA(cudaMemcpyAsync(s->d_X[0].p, s->d_X[2].p, 3 * (size_t)s->P_local * 8, cudaMemcpyDeviceToDevice, st));
+    XRB_CUDA(cudaStreamSynchronize(st));
+    return XRB_OK;
+}
+
+int xrb_ba_run(xrb_ba_solver *s, const xrb_ba_options *opt, xrb_ba_summary *summary, void *stream) {
+    if (!s || !opt || !summary) return XRB_ERR_INVALID;
+    return do_run(s, opt, summary, stream ? (cudaStream_t)stream : s->own_stream);
+}
+
+int xrb_ba_fetch(xrb_ba_solver *s, xrb_ba_problem *prob) {
+    if (!s) return XRB_ERR_INVALID;
+    return do_fetch(s, prob);
+}
+
+int xrb_ba_solve(xrb_ba_solver *s, const xrb_ba_problem *prob, const xrb_ba_options *opt,
+                 xrb_ba_summary *summary) {
+    if (!s || !prob || !opt || !summary) return XRB_ERR_INVALID;
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = do_load(s, prob);
+    if (rc) return rc;
+    if ((rc = do_run(s, opt, summary, s->own_stream))) return rc;
+    if ((rc = do_fetch(s, const_cast<xrb_ba_problem *>(prob)))) return rc;
+    summary->total_time_in_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return XRB_OK;
+}
+
+int xrb_ba_residuals(xrb_ba_solver *s, double *out) {
+    if (!s || !s->loaded || !out) return XRB_ERR_INVALID;
+    XRB_CUDA(cudaSetDevice(s->device));
+    if (s->world > 1) {
+        set_error("ba_residuals: single-GPU only");
+        return XRB_ERR_INVALID;
+    }
+    cudaStream_t st = s->own_stream;
+    DevBuf tmp;
+    int rc = tmp.reserve(std::max<size_t>(1, 2 * (size_t)s->O_total) * 8);
+    if (rc) return rc;
+    BAConsts k{5.99, 5.99 * 5.99, 1e-2, 12.0};
+    rc = ba_launch_residuals(s->prob(), s->state(s->cur), k, s->d_obs_orig.as<int32_t>(), tmp.as<double>(), st);
+    if (rc == XRB_OK && cudaMemcpyAsync(out, tmp.p, 2 * (size_t)s->O_total * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        rc = XRB_ERR_CUDA;
+    cudaStreamSynchronize(st);
+    tmp.release();
+    return rc;
+}
+
+int xrb_ba_profile(const xrb_ba_solver *s, double ms[6], int64_t launches[6]) {
+    if (!s) return XRB_ERR_INVALID;
+    for (int i = 0; i < 6; ++i) {
+        if (ms) ms[i] = s->ms[i];
+        if (launches) launches[i] = s->launches[i];
+    }
+    return XRB_OK;
+}
+
+}  // extern "C"

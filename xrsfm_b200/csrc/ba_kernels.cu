@@ -1,0 +1,769 @@
+// ba_kernels.cu — per-observation model and the point-major LM kernels of path B.
+// See ba_kernels.cuh for the pipeline and DESIGN.md §B for layout and rooflines.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+
+#include "ba_kernels.cuh"
+
+namespace xrb {
+
+// =====================================================================================
+// Per-observation model: ReProjectionCost::operator() (cost_factor_ceres.h:19-40) with the
+// Jacobians Ceres' autodiff + EigenQuaternionParameterization produce, in closed form, and
+// HuberLoss(a) + Corrector (rho'' < 0 always, so the correction is a plain sqrt(rho') scale).
+// =====================================================================================
+
+// uv = WorldToImage(params, xy) and D = d(uv)/d(xy) (row-major 2x2) for model ids 0..4
+// (camera_model.hpp:93-210).  Ids 0/1 keep the reference quirk Distortion() = xy => 2 f x + c.
+__device__ __forceinline__ void world_to_image(int model, const double *__restrict__ p, double x,
+                                               double y, double &u, double &v, double D[4]) {
+    if (model == 2 || model == 3) {
+        const double fx = p[0], fy = model == 2 ? p[0] : p[1];
+        const double cx = model == 2 ? p[1] : p[2], cy = model == 2 ? p[2] : p[3];
+        const double k = model == 2 ? p[3] : p[4];
+        const double r2 = x * x + y * y, radial = k * r2;
+        u = fx * (x + x * radial) + cx;
+        v = fy * (y + y * radial) + cy;
+        const double kxy2 = 2.0 * k * x * y;
+        D[0] = fx * (1.0 + radial + 2.0 * k * x * x), D[1] = fx * kxy2;
+        D[2] = fy * kxy2, D[3] = fy * (1.0 + radial + 2.0 * k * y * y);
+    } else if (model == 0) {
+        u = p[0] * (x + x) + p[1], v = p[0] * (y + y) + p[2];
+        D[0] = 2.0 * p[0], D[1] = 0.0, D[2] = 0.0, D[3] = 2.0 * p[0];
+    } else if (model == 1) {
+        u = p[0] * (x + x) + p[2], v = p[1] * (y + y) + p[3];
+        D[0] = 2.0 * p[0], D[1] = 0.0, D[2] = 0.0, D[3] = 2.0 * p[1];
+    } else {  // OpenCV: fx fy cx cy k1 k2 p1 p2
+        const double fx = p[0], fy = p[1], k1 = p[4], k2 = p[5], p1 = p[6], p2 = p[7];
+        const double x2 = x * x, xy = x * y, y2 = y * y, r2 = x2 + y2;
+        const double radial = k1 * r2 + k2 * r2 * r2;
+        const double du = x * radial + 2.0 * p1 * xy + p2 * (r2 + 2.0 * x2);
+        const double dv = y * radial + 2.0 * p2 * xy + p1 * (r2 + 2.0 * y2);
+        u = fx * (x + du) + p[2], v = fy * (y + dv) + p[3];
+        const double dr = k1 + 2.0 * k2 * r2;
+        const double ddu_dx = radial + 2.0 * x2 * dr + 2.0 * p1 * y + 6.0 * p2 * x;
+        const double ddu_dy = 2.0 * xy * dr + 2.0 * p1 * x + 2.0 * p2 * y;
+        const double ddv_dx = 2.0 * xy * dr + 2.0 * p2 * y + 2.0 * p1 * x;
+        const double ddv_dy = radial + 2.0 * y2 * dr + 2.0 * p2 * x + 6.0 * p1 * y;
+        D[0] = fx * (1.0 + ddu_dx), D[1] = fx * ddu_dy, D[2] = fy * ddv_dx, D[3] = fy * (1.0 + ddv_dy);
+    }
+}
+
+struct Obs {
+    double r0, r1;   // residual (robustified when requested)
+    double Jd[6];    // 2x3 d r / d(quaternion tangent)
+    double Jt[6];    // 2x3 d r / d t
+    double JX[6];    // 2x3 d r / d X
+    double rho0;     // rho(s)
+};
+
+template <bool kJac>
+__device__ __forceinline__ void eval_obs(const double *__restrict__ q, const double *__restrict__ t,
+                                         const double *__restrict__ X, int model,
+                                         const double *__restrict__ intr, double um, double vm,
+                                         const BAConsts &k, bool robustify, Obs &e) {
+    const double ux = q[0], uy = q[1], uz = q[2], w = q[3];
+    const double X0 = X[0], X1 = X[1], X2 = X[2];
+    // Eigen Quaternion::_transformVector: uv = 2 (u x v); pc = v + w uv + u x uv
+    const double c0 = 2.0 * (uy * X2 - uz * X1);
+    const double c1 = 2.0 * (uz * X0 - ux * X2);
+    const double c2 = 2.0 * (ux * X1 - uy * X0);
+    const double pcx = X0 + w * c0 + (uy * c2 - uz * c1) + t[0];
+    const double pcy = X1 + w * c1 + (uz * c0 - ux * c2) + t[1];
+    const double pcz = X2 + w * c2 + (ux * c1 - uy * c0) + t[2];
+    if (pcz < k.min_depth) {  // cost_factor_ceres.h:29-31: constant residual, zero Jacobian
+        e.r0 = e.r1 = k.neg_depth_residual;
+        if (kJac) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) e.Jd[i] = e.Jt[i] = e.JX[i] = 0.0;
+        }
+    } else {
+        const double iz = 1.0 / pcz, x = pcx * iz, y = pcy * iz;
+        double u, v, D[4];
+        world_to_image(model, intr, x, y, u, v, D);
+        e.r0 = u - um, e.r1 = v - vm;
+        if (kJac) {
+            double A[6];
+            A[0] = D[0] * iz, A[1] = D[1] * iz, A[2] = -(D[0] * x + D[1] * y) * iz;
+            A[3] = D[2] * iz, A[4] = D[3] * iz, A[5] = -(D[2] * x + D[3] * y) * iz;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) e.Jt[i] = A[i];
+            // d pc/dX = I + 2w[u]x + 2[u]x[u]x  (== R(q) on the unit sphere)
+            const double uu = ux * ux + uy * uy + uz * uz;
+            const double M0 = 1.0 + 2.0 * (ux * ux - uu), M1 = 2.0 * (ux * uy - w * uz), M2 = 2.0 * (ux * uz + w * uy);
+            const double M3 = 2.0 * (ux * uy + w * uz), M4 = 1.0 + 2.0 * (uy * uy - uu), M5 = 2.0 * (uy * uz - w * ux);
+            const double M6 = 2.0 * (ux * uz - w * uy), M7 = 2.0 * (uy * uz + w * ux), M8 = 1.0 + 2.0 * (uz * uz - uu);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                e.JX[r * 3 + 0] = A[r * 3] * M0 + A[r * 3 + 1] * M3 + A[r * 3 + 2] * M6;
+                e.JX[r * 3 + 1] = A[r * 3] * M1 + A[r * 3 + 1] * M4 + A[r * 3 + 2] * M7;
+                e.JX[r * 3 + 2] = A[r * 3] * M2 + A[r * 3 + 1] * M5 + A[r * 3 + 2] * M8;
+            }
+            // G = d pc / d(x,y,z,w):  d/du = -2w[v]x + 2((u.v)I + u v^T - 2 v u^T), d/dw = 2(u x v)
+            const double udv = ux * X0 + uy * X1 + uz * X2;
+            double G[12];
+            G[0] = 2.0 * (udv + ux * X0 - 2.0 * X0 * ux);
+            G[1] = 2.0 * (w * X2 + ux * X1 - 2.0 * X0 * uy);
+            G[2] = 2.0 * (-w * X1 + ux * X2 - 2.0 * X0 * uz);
+            G[3] = c0;
+            G[4] = 2.0 * (-w * X2 + uy * X0 - 2.0 * X1 * ux);
+            G[5] = 2.0 * (udv + uy * X1 - 2.0 * X1 * uy);
+            G[6] = 2.0 * (w * X0 + uy * X2 - 2.0 * X1 * uz);
+            G[7] = c1;
+            G[8] = 2.0 * (w * X1 + uz * X0 - 2.0 * X2 * ux);
+            G[9] = 2.0 * (-w * X0 + uz * X1 - 2.0 * X2 * uy);
+            G[10] = 2.0 * (udv + uz * X2 - 2.0 * X2 * uz);
+            G[11] = c2;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const double j0 = A[r * 3] * G[0] + A[r * 3 + 1] * G[4] + A[r * 3 + 2] * G[8];
+                const double j1 = A[r * 3] * G[1] + A[r * 3 + 1] * G[5] + A[r * 3 + 2] * G[9];
+                const double j2 = A[r * 3] * G[2] + A[r * 3 + 1] * G[6] + A[r * 3 + 2] * G[10];
+                const double j3 = A[r * 3] * G[3] + A[r * 3 + 1] * G[7] + A[r * 3 + 2] * G[11];
+                // EigenQuaternionParameterization::ComputeJacobian (4x3, row-major):
+                //   [ w, z,-y; -z, w, x;  y,-x, w; -x,-y,-z ]
+                e.Jd[r * 3 + 0] = j0 * w - j1 * uz + j2 * uy - j3 * ux;
+                e.Jd[r * 3 + 1] = j0 * uz + j1 * w - j2 * ux - j3 * uy;
+                e.Jd[r * 3 + 2] = -j0 * uy + j1 * ux + j2 * w - j3 * uz;
+            }
+        }
+    }
+    const double s = e.r0 * e.r0 + e.r1 * e.r1;
+    double rho1 = 1.0;
+    if (s > k.huber_b) {  // HuberLoss::Evaluate
+        const double rt = sqrt(s);
+        e.rho0 = 2.0 * k.huber_a * rt - k.huber_b;
+        rho1 = fmax(DBL_MIN, k.huber_a / rt);
+    } else {
+        e.rho0 = s;
+    }
+    if (robustify && rho1 != 1.0) {  // Corrector, alpha == 0 branch
+        const double sc = sqrt(rho1);
+        e.r0 *= sc, e.r1 *= sc;
+        if (kJac) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) e.Jd[i] *= sc, e.Jt[i] *= sc, e.JX[i] *= sc;
+        }
+    }
+}
+
+// EigenQuaternionParameterization::Plus: x+ = dq (x) x, dq = (sin|d|/|d| d, cos|d|)
+__device__ __forceinline__ void quat_plus(const double *q, double d0, double d1, double d2,
+                                          double out[4]) {
+    const double n = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    if (n > 0.0) {
+        const double sbd = sin(n) / n;
+        const double ax = sbd * d0, ay = sbd * d1, az = sbd * d2, aw = cos(n);
+        const double bx = q[0], by = q[1], bz = q[2], bw = q[3];
+        out[0] = aw * bx + ax * bw + ay * bz - az * by;
+        out[1] = aw * by - ax * bz + ay * bw + az * bx;
+        out[2] = aw * bz + ax * by - ay * bx + az * bw;
+        out[3] = aw * bw - ax * bx - ay * by - az * bz;
+    } else {
+        out[0] = q[0], out[1] = q[1], out[2] = q[2], out[3] = q[3];
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    return v;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double *addr, double v) {
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long *>(addr),
+              (unsigned long long)__double_as_longlong(v));
+}
+
+// Scaled, robustified blocks of one observation: Jc[12] = [Jd | Jt] (2x6, zero where the
+// camera block is constant), JX scaled by the point's Jacobi scale (zero for constant points).
+struct LinObs {
+    double Jc[12];
+    double JX[6];
+    double r0, r1;
+    int cols[6];
+    bool active;
+};
+
+__device__ __forceinline__ void lin_obs(const BAProblemDev &P, const BAStateDev &x,
+                                        const BAConsts &k, const BALinSys &L, int o, int p,
+                                        bool pvar, LinObs &lo) {
+    const int c = P.obs_cam[o];
+    const int cq = P.colq[c], ct = P.colt[c];
+    lo.active = cq >= 0 || ct >= 0 || pvar;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) lo.cols[j] = cq >= 0 ? cq + j : -1, lo.cols[3 + j] = ct >= 0 ? ct + j : -1;
+    if (!lo.active) return;
+    const int ii = P.cam_intr[c];
+    Obs e;
+    eval_obs<true>(x.q + 4 * (size_t)c, x.t + 3 * (size_t)c, x.X + 3 * (size_t)p, P.intr_model[ii],
+                   P.intr + 8 * (size_t)ii, P.obs_uv[2 * (size_t)o], P.obs_uv[2 * (size_t)o + 1], k,
+                   true, e);
+    lo.r0 = e.r0, lo.r1 = e.r1;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            lo.Jc[r * 6 + j] = cq >= 0 ? e.Jd[r * 3 + j] * L.sc[cq + j] : 0.0;
+            lo.Jc[r * 6 + 3 + j] = ct >= 0 ? e.Jt[r * 3 + j] * L.sc[ct + j] : 0.0;
+            lo.JX[r * 3 + j] = pvar ? e.JX[r * 3 + j] * L.sp[3 * (size_t)p + j] : 0.0;
+        }
+}
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kChunk = 32;  // observations of one point handled per pass (one per lane)
+
+// =====================================================================================
+// 1. Jacobi scaling (iteration 0): squared column norms of the robustified Jacobian.
+//    Point columns are local to the point; camera columns are accumulated with atomics and
+//    finished (after the all-reduce in multi-GPU mode) by k_finish_scaling.
+// =====================================================================================
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_colnorm(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int p = warp; p < P.n_pts_local; p += nwarps) {
+        const int k0 = P.pt_ptr[p], kn = P.pt_ptr[p + 1] - k0;
+        const bool pvar = P.pt_var[p] != 0;
+        double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+        for (int base = 0; base < kn; base += kChunk) {
+            const int i = base + lane;
+            if (i < kn) {
+                LinObs lo;
+                lin_obs(P, x, k, L, k0 + i, p, pvar, lo);  // sc == sp == 1 at this point
+                if (lo.active) {
+#pragma unroll
+                    for (int j = 0; j < 6; ++j)
+                        if (lo.cols[j] >= 0)
+                            atomicAdd(&L.n2c[lo.cols[j]], lo.Jc[j] * lo.Jc[j] + lo.Jc[6 + j] * lo.Jc[6 + j]);
+                    n0 += lo.JX[0] * lo.JX[0] + lo.JX[3] * lo.JX[3];
+                    n1 += lo.JX[1] * lo.JX[1] + lo.JX[4] * lo.JX[4];
+                    n2 += lo.JX[2] * lo.JX[2] + lo.JX[5] * lo.JX[5];
+                }
+            }
+        }
+        n0 = warp_sum(n0), n1 = warp_sum(n1), n2 = warp_sum(n2);
+        if (lane == 0 && pvar) {
+            L.sp[3 * (size_t)p + 0] = 1.0 / (1.0 + sqrt(n0));
+            L.sp[3 * (size_t)p + 1] = 1.0 / (1.0 + sqrt(n1));
+            L.sp[3 * (size_t)p + 2] = 1.0 / (1.0 + sqrt(n2));
+        }
+    }
+}
+
+__global__ void k_finish_scaling(int nc, const double *__restrict__ n2c, double *__restrict__ sc) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nc) sc[j] = 1.0 / (1.0 + sqrt(n2c[j]));
+}
+
+static int point_grid(int n_pts) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int want = (n_pts + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int cap = sms * 16;  // persistent-ish: a multiple of the SM count
+    return want < cap ? (want > 0 ? want : 1) : cap;
+}
+
+int ba_launch_colnorm(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
+                      const BALinSys &L, cudaStream_t st) {
+    if (P.n_pts_local > 0) {
+        k_colnorm<<<point_grid(P.n_pts_local), kWarpsPerCta * 32, 0, st>>>(P, x, k, L);
+        XRB_LAUNCHED();
+    }
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+int ba_launch_finish_scaling(const BAProblemDev &P, const BALinSys &L, cudaStream_t st) {
+    if (P.nc > 0) {
+        k_finish_scaling<<<(P.nc + 255) / 256, 256, 0, st>>>(P.nc, L.n2c, L.sc);
+        XRB_LAUNCHED();
+    }
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+// =====================================================================================
+// 2. Fused linearise + Schur complement.  One warp per point, one observation per lane.
+//    Phase A: r, J, Huber; V = sum JX^T JX, g = sum JX^T r by warp shuffles.
+//    Phase B: V + D_p^2 (LM diagonal of the point block) inverted in registers.
+//    Phase C: per observation W = Jc^T JX (6x3), T = W V^-1 staged in shared memory;
+//             U_c += Jc^T Jc, g_c += Jc^T r, rhs_c += Jc^T r - T g  (FP64 atomics).
+//    Phase D: S[c_i,c_j] -= T_i W_j^T for every unordered observation pair of the point,
+//             36 entries per pair spread over the lanes, FP64 atomics into the lower triangle.
+// =====================================================================================
+struct __align__(16) WarpStage {
+    double T[kChunk][18];
+    double W[kChunk][18];
+    int colsA[kChunk][6];
+    int colsB[kChunk][6];
+};
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_schur(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L, double inv_radius,
+        double *__restrict__ scalars) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpStage &sm = reinterpret_cast<WarpStage *>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int n = P.nc, ld = L.ld;
+    double *rhs = L.S + (size_t)n * ld;
+    double gmax = 0.0;
+
+    for (int p = warp; p < P.n_pts_local; p += nwarps) {
+        const int k0 = P.pt_ptr[p], kn = P.pt_ptr[p + 1] - k0;
+        if (kn == 0) continue;
+        const bool pvar = P.pt_var[p] != 0;
+        const int nchunks = (kn + kChunk - 1) / kChunk;
+        // ---- Phase A
+        double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+        LinObs lo;  // stays live for the single-chunk case
+        lo.active = false;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int i = ch * kChunk + lane;
+            lo.active = false;
+            if (i < kn) lin_obs(P, x, k, L, k0 + i, p, pvar, lo);
+            if (lo.active) {
+                const double *J = lo.JX;
+                V[0] += J[0] * J[0] + J[3] * J[3], V[1] += J[0] * J[1] + J[3] * J[4];
+                V[2] += J[0] * J[2] + J[3] * J[5], V[3] += J[1] * J[1] + J[4] * J[4];
+                V[4] += J[1] * J[2] + J[4] * J[5], V[5] += J[2] * J[2] + J[5] * J[5];
+                g[0] += J[0] * lo.r0 + J[3] * lo.r1;
+                g[1] += J[1] * lo.r0 + J[4] * lo.r1;
+                g[2] += J[2] * lo.r0 + J[5] * lo.r1;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) V[j] = warp_sum(V[j]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) g[j] = warp_sum(g[j]);
+        // ---- Phase B: (V + D^2)^-1, D^2 = clamp(diag V, 1e-6, 1e32) / radius
+        double Vi[6] = {0, 0, 0, 0, 0, 0};
+        if (pvar) {
+            const double a = V[0] + fmin(fmax(V[0], 1e-6), 1e32) * inv_radius;
+            const double d = V[3] + fmin(fmax(V[3], 1e-6), 1e32) * inv_radius;
+            const double f = V[5] + fmin(fmax(V[5], 1e-6), 1e32) * inv_radius;
+            const double b = V[1], c = V[2], e = V[4];
+            const double A = d * f - e * e, B = c * e - b * f, Cc = b * e - c * d;
+            const double det = a * A + b * B + c * Cc;
+            const double id = 1.0 / det;
+            Vi[0] = A * id, Vi[1] = B * id, Vi[2] = Cc * id;
+            Vi[3] = (a * f - c * c) * id, Vi[4] = (b * c - a * e) * id, Vi[5] = (a * d - b * b) * id;
+            if (lane == 0) {
+                if (!(fabs(det) > 0.0) || !isfinite(id)) scalars[SC_FAIL] = 1.0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) L.Vinv[6 * (size_t)p + j] = Vi[j];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) L.gp[3 * (size_t)p + j] = g[j];
+                const double *s = L.sp + 3 * (size_t)p;
+                gmax = fmax(gmax, fmax(fabs(g[0] / s[0]), fmax(fabs(g[1] / s[1]), fabs(g[2] / s[2]))));
+            }
+        }
+        // ---- Phases C + D over chunk pairs (a single pass when kn <= 32)
+        for (int ca = 0; ca < nchunks; ++ca) {
+            const int ia = ca * kChunk + lane;
+            const int na = min(kChunk, kn - ca * kChunk);
+            if (nchunks > 1) {  // re-linearise chunk ca (registers were overwritten)
+                lo.active = false;
+                if (ia < kn) lin_obs(P, x, k, L, k0 + ia, p, pvar, lo);
+            }
+            double Wr[18];
+            __syncwarp();
+            if (ia < kn) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) sm.colsA[lane][j] = lo.active ? lo.cols[j] : -1;
+            }
+            if (ia < kn && lo.active) {
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) Wr[a * 3 + b] = lo.Jc[a] * lo.JX[b] + lo.Jc[6 + a] * lo.JX[3 + b];
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    const double t0 = Wr[a * 3] * Vi[0] + Wr[a * 3 + 1] * Vi[1] + Wr[a * 3 + 2] * Vi[2];
+                    const double t1 = Wr[a * 3] * Vi[1] + Wr[a * 3 + 1] * Vi[3] + Wr[a * 3 + 2] * Vi[4];
+                    const double t2 = Wr[a * 3] * Vi[2] + Wr[a * 3 + 1] * Vi[4] + Wr[a * 3 + 2] * Vi[5];
+                    sm.T[lane][a * 3] = t0, sm.T[lane][a * 3 + 1] = t1, sm.T[lane][a * 3 + 2] = t2;
+                    const int col = lo.cols[a];
+                    if (col >= 0) {
+                        // camera block-diagonal row (6 wide), gradient and reduced rhs
+#pragma unroll
+                        for (int b = 0; b < 6; ++b)
+                            if (lo.cols[b] >= 0 && b <= a)
+                                atomicAdd(&L.U[(size_t)col * 6 + b], lo.Jc[a] * lo.Jc[b] + lo.Jc[6 + a] * lo.Jc[6 + b]);
+                        const double gr = lo.Jc[a] * lo.r0 + lo.Jc[6 + a] * lo.r1;
+                        atomicAdd(&L.gc[col], gr);
+                        atomicAdd(&rhs[col], gr - (t0 * g[0] + t1 * g[1] + t2 * g[2]));
+                    }
+                }
+            }
+            if (!pvar) continue;  // constant point: no elimination, only the F^T F terms above
+            for (int cb = 0; cb <= ca; ++cb) {
+                const int nb = min(kChunk, kn - cb * kChunk);
+                __syncwarp();
+                if (cb == ca) {
+                    if (ia < kn) {
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) sm.colsB[lane][j] = sm.colsA[lane][j];
+                        if (lo.active) {
+#pragma unroll
+                            for (int j = 0; j < 18; ++j) sm.W[lane][j] = Wr[j];
+                        }
+                    }
+                } else {
+                    const int ib = cb * kChunk + lane;
+                    LinObs lb;
+                    lb.active = false;
+                    if (ib < kn) lin_obs(P, x, k, L, k0 + ib, p, pvar, lb);
+                    if (ib < kn) {
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) sm.colsB[lane][j] = lb.active ? lb.cols[j] : -1;
+                        if (lb.active) {
+#pragma unroll
+                            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                                for (int b = 0; b < 3; ++b)
+                                    sm.W[lane][a * 3 + b] = lb.Jc[a] * lb.JX[b] + lb.Jc[6 + a] * lb.JX[3 + b];
+                        }
+                    }
+                }
+                __syncwarp();
+                // unordered pairs {i in chunk a, j in chunk b}; same chunk: j <= i
+                const int npairs = (cb == ca) ? na * (na + 1) / 2 : na * nb;
+                for (int it = lane; it < npairs * 36; it += 32) {
+                    const int pr = it / 36, e = it - pr * 36;
+                    int i, j;
+                    if (cb == ca) {
+                        i = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
+                        while (i * (i + 1) / 2 > pr) --i;
+                        while ((i + 1) * (i + 2) / 2 <= pr) ++i;
+                        j = pr - i * (i + 1) / 2;
+                    } else {
+                        i = pr / nb, j = pr - i * nb;
+                    }
+                    const int a = e / 6, b = e - a * 6;
+                    const bool same_obs = (cb == ca) && (i == j);
+                    if (same_obs && b > a) continue;  // symmetric block: lower entries once
+                    const int r = sm.colsA[i][a], c = sm.colsB[j][b];
+                    if (r < 0 || c < 0) continue;
+                    double val = sm.T[i][a * 3] * sm.W[j][b * 3] + sm.T[i][a * 3 + 1] * sm.W[j][b * 3 + 1] +
+                                 sm.T[i][a * 3 + 2] * sm.W[j][b * 3 + 2];
+                    // two observations of the same camera: the block is M + M^T, whose
+                    // diagonal is 2 M_aa (the off-diagonal pairs land on the same entry)
+                    if (!same_obs && r == c) val *= 2.0;
+                    const int hi = r >= c ? r : c, lo_ = r >= c ? c : r;
+                    atomicAdd(&L.S[(size_t)hi * ld + lo_], -val);
+                }
+            }
+        }
+    }
+    if (lane == 0 && gmax > 0.0) atomic_max_nonneg(&scalars[SC_GRAD_MAX_PT], gmax);
+}
+
+int ba_launch_schur(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
+                    const BALinSys &L, double inv_radius, double *scalars, cudaStream_t st) {
+    if (P.n_pts_local > 0) {
+        const size_t smem = sizeof(WarpStage) * kWarpsPerCta;
+        static bool attr_set = false;
+        if (!attr_set) {
+            XRB_CUDA(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        k_schur<<<point_grid(P.n_pts_local), kWarpsPerCta * 32, smem, st>>>(P, x, k, L, inv_radius, scalars);
+        XRB_LAUNCHED();
+    }
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+// =====================================================================================
+// 3a. Camera block-diagonal: S += U + D_c^2 with D_c^2 = clamp(diag U, 1e-6, 1e32)/radius,
+//     and the camera part of the gradient max-norm ||x - Plus(x, -g)||_inf.
+//     Runs after the exchange (U, gc are global sums).
+// =====================================================================================
+__global__ void k_cam_diag(BAProblemDev P, BAStateDev x, BALinSys L, double inv_radius,
+                           double *__restrict__ scalars) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.n_cams) return;
+    const int cq = P.colq[c], ct = P.colt[c];
+    int cols[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) cols[j] = cq >= 0 ? cq + j : -1, cols[3 + j] = ct >= 0 ? ct + j : -1;
+    const int ld = L.ld;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        if (cols[a] < 0) continue;
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+            if (cols[b] < 0) continue;
+            double v = L.U[(size_t)cols[a] * 6 + b];
+            if (a == b) v += fmin(fmax(v, 1e-6), 1e32) * inv_radius;
+            L.S[(size_t)cols[a] * ld + cols[b]] += v;
+        }
+    }
+    double gmax = 0.0;
+    if (cq >= 0) {
+        double qn[4];
+        const double *q = x.q + 4 * (size_t)c;
+        quat_plus(q, -L.gc[cq] / L.sc[cq], -L.gc[cq + 1] / L.sc[cq + 1], -L.gc[cq + 2] / L.sc[cq + 2], qn);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gmax = fmax(gmax, fabs(q[j] - qn[j]));
+    }
+    if (ct >= 0)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gmax = fmax(gmax, fabs(L.gc[ct + j] / L.sc[ct + j]));
+    if (gmax > 0.0) atomic_max_nonneg(&scalars[SC_GRAD_MAX_CAM], gmax);
+}
+
+int ba_launch_cam_diag(const BAProblemDev &P, const BAStateDev &x, const BALinSys &L,
+                       double inv_radius, double *scalars, cudaStream_t st) {
+    k_cam_diag<<<(P.n_cams + 127) / 128, 128, 0, st>>>(P, x, L, inv_radius, scalars);
+    XRB_LAUNCHED();
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+// =====================================================================================
+// 4. Back-substitution y_p = V^-1 (g_p - sum W_i^T y_c), candidate point, model cost change
+//    -(J s)^T (r + J s / 2) and step / state norms, one warp per point.
+// =====================================================================================
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_backsub(BAProblemDev P, BAStateDev x, BAStateDev cand, BAConsts k, BALinSys L,
+          const double *__restrict__ yc, double *__restrict__ step_p, double *__restrict__ scalars) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    double model = 0.0, sn2 = 0.0, xn2 = 0.0;
+    for (int p = warp; p < P.n_pts_local; p += nwarps) {
+        const int k0 = P.pt_ptr[p], kn = P.pt_ptr[p + 1] - k0;
+        const bool pvar = P.pt_var[p] != 0;
+        const int nchunks = (kn + kChunk - 1) / kChunk;
+        double acc0 = 0, acc1 = 0, acc2 = 0;
+        LinObs lo;
+        lo.active = false;
+        double jy0 = 0, jy1 = 0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int i = ch * kChunk + lane;
+            lo.active = false;
+            if (i < kn) lin_obs(P, x, k, L, k0 + i, p, pvar, lo);
+            jy0 = jy1 = 0.0;
+            if (lo.active) {
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+                    if (lo.cols[a] >= 0) {
+                        const double y = yc[lo.cols[a]];
+                        jy0 += lo.Jc[a] * y, jy1 += lo.Jc[6 + a] * y;
+                    }
+                acc0 += lo.JX[0] * jy0 + lo.JX[3] * jy1;
+                acc1 += lo.JX[1] * jy0 + lo.JX[4] * jy1;
+                acc2 += lo.JX[2] * jy0 + lo.JX[5] * jy1;
+            }
+        }
+        acc0 = warp_sum(acc0), acc1 = warp_sum(acc1), acc2 = warp_sum(acc2);
+        double y0 = 0, y1 = 0, y2 = 0;
+        if (pvar) {
+            const double *Vi = L.Vinv + 6 * (size_t)p;
+            const double b0 = L.gp[3 * (size_t)p] - acc0, b1 = L.gp[3 * (size_t)p + 1] - acc1,
+                         b2 = L.gp[3 * (size_t)p + 2] - acc2;
+            y0 = Vi[0] * b0 + Vi[1] * b1 + Vi[2] * b2;
+            y1 = Vi[1] * b0 + Vi[3] * b1 + Vi[4] * b2;
+            y2 = Vi[2] * b0 + Vi[4] * b1 + Vi[5] * b2;
+            if (lane == 0) {
+                const double *s = L.sp + 3 * (size_t)p;
+                const double *X = x.X + 3 * (size_t)p;
+                double *Xc = cand.X + 3 * (size_t)p;
+                const double d0 = -y0 * s[0], d1 = -y1 * s[1], d2 = -y2 * s[2];
+                step_p[3 * (size_t)p] = -y0, step_p[3 * (size_t)p + 1] = -y1, step_p[3 * (size_t)p + 2] = -y2;
+                Xc[0] = X[0] + d0, Xc[1] = X[1] + d1, Xc[2] = X[2] + d2;
+                const double e0 = X[0] - Xc[0], e1 = X[1] - Xc[1], e2 = X[2] - Xc[2];
+                sn2 += e0 * e0 + e1 * e1 + e2 * e2;
+                xn2 += Xc[0] * Xc[0] + Xc[1] * Xc[1] + Xc[2] * Xc[2];
+                if (!isfinite(y0) || !isfinite(y1) || !isfinite(y2)) scalars[SC_FAIL] = 1.0;
+            }
+        } else if (lane == 0) {
+            const double *X = x.X + 3 * (size_t)p;
+            double *Xc = cand.X + 3 * (size_t)p;
+            Xc[0] = X[0], Xc[1] = X[1], Xc[2] = X[2];
+        }
+        // model residual m = J s = -(Jc yc + JX yp); contribution -(m . (r + m / 2))
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int i = ch * kChunk + lane;
+            if (nchunks > 1) {
+                lo.active = false;
+                if (i < kn) lin_obs(P, x, k, L, k0 + i, p, pvar, lo);
+                jy0 = jy1 = 0.0;
+                if (lo.active) {
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+                        if (lo.cols[a] >= 0) {
+                            const double y = yc[lo.cols[a]];
+                            jy0 += lo.Jc[a] * y, jy1 += lo.Jc[6 + a] * y;
+                        }
+                }
+            }
+            if (lo.active) {
+                const double m0 = -(jy0 + lo.JX[0] * y0 + lo.JX[1] * y1 + lo.JX[2] * y2);
+                const double m1 = -(jy1 + lo.JX[3] * y0 + lo.JX[4] * y1 + lo.JX[5] * y2);
+                model -= m0 * (lo.r0 + 0.5 * m0) + m1 * (lo.r1 + 0.5 * m1);
+            }
+        }
+    }
+    model = warp_sum(model);
+    if (lane == 0) {
+        atomicAdd(&scalars[SC_MODEL_CHANGE], model);
+        atomicAdd(&scalars[SC_STEP_NORM2], sn2);
+        atomicAdd(&scalars[SC_XNORM2], xn2);
+    }
+}
+
+int ba_launch_backsub(const BAProblemDev &P, const BAStateDev &x, const BAStateDev &cand,
+                      const BAConsts &k, const BALinSys &L, const double *yc, double *step_p,
+                      double *scalars, cudaStream_t st) {
+    if (P.n_pts_local > 0) {
+        k_backsub<<<point_grid(P.n_pts_local), kWarpsPerCta * 32, 0, st>>>(P, x, cand, k, L, yc, step_p, scalars);
+        XRB_LAUNCHED();
+    }
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+// Camera candidate: q+ = Plus(q, -y_q * scale), t+ = t - y_t * scale; norms of the camera part.
+__global__ void k_cam_update(BAProblemDev P, BAStateDev x, BAStateDev cand, BALinSys L,
+                             const double *__restrict__ yc, double *__restrict__ scalars,
+                             int add_norms) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    double sn2 = 0.0, xn2 = 0.0;
+    if (c < P.n_cams) {
+        const int cq = P.colq[c], ct = P.colt[c];
+        const double *q = x.q + 4 * (size_t)c, *t = x.t + 3 * (size_t)c;
+        double *qc = cand.q + 4 * (size_t)c, *tc = cand.t + 3 * (size_t)c;
+        if (cq >= 0) {
+            double qn[4];
+            quat_plus(q, -yc[cq] * L.sc[cq], -yc[cq + 1] * L.sc[cq + 1], -yc[cq + 2] * L.sc[cq + 2], qn);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                qc[j] = qn[j];
+                sn2 += (q[j] - qn[j]) * (q[j] - qn[j]);
+                xn2 += qn[j] * qn[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) qc[j] = q[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (ct >= 0) {
+                const double v = t[j] - yc[ct + j] * L.sc[ct + j];
+                tc[j] = v;
+                sn2 += (t[j] - v) * (t[j] - v);
+                xn2 += v * v;
+            } else {
+                tc[j] = t[j];
+            }
+        }
+    }
+    if (add_norms) {
+        sn2 = warp_sum(sn2), xn2 = warp_sum(xn2);
+        if ((threadIdx.x & 31) == 0 && (sn2 != 0.0 || xn2 != 0.0)) {
+            atomicAdd(&scalars[SC_STEP_NORM2], sn2);
+            atomicAdd(&scalars[SC_XNORM2], xn2);
+        }
+    }
+}
+
+int ba_launch_cam_update(const BAProblemDev &P, const BAStateDev &x, const BAStateDev &cand,
+                         const BALinSys &L, const double *yc, double *scalars, int add_norms,
+                         cudaStream_t st) {
+    k_cam_update<<<(P.n_cams + 127) / 128, 128, 0, st>>>(P, x, cand, L, yc, scalars, add_norms);
+    XRB_LAUNCHED();
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+// =====================================================================================
+// 5. Cost 1/2 sum rho over observations (thread per observation, point looked up by
+//    binary search in pt_ptr so the observation stream stays coalesced).
+// =====================================================================================
+__device__ __forceinline__ int point_of_obs(const int32_t *__restrict__ pt_ptr, int n_pts, int o) {
+    int lo = 0, hi = n_pts;  // largest p with pt_ptr[p] <= o
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pt_ptr[mid] <= o)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+k_cost(BAProblemDev P, BAStateDev x, BAConsts k, int mode, double *__restrict__ out) {
+    double s = 0.0;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < P.n_obs_local; o += gridDim.x * blockDim.x) {
+        const int p = point_of_obs(P.pt_ptr, P.n_pts_local, o);
+        const int c = P.obs_cam[o];
+        const bool active = P.colq[c] >= 0 || P.colt[c] >= 0 || P.pt_var[p] != 0;
+        if (active != (mode == 0)) continue;
+        const int ii = P.cam_intr[c];
+        Obs e;
+        eval_obs<false>(x.q + 4 * (size_t)c, x.t + 3 * (size_t)c, x.X + 3 * (size_t)p, P.intr_model[ii],
+                        P.intr + 8 * (size_t)ii, P.obs_uv[2 * (size_t)o], P.obs_uv[2 * (size_t)o + 1], k,
+                        false, e);
+        s += 0.5 * e.rho0;
+    }
+    __shared__ double wsum[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double v = wsum[threadIdx.x];
+#pragma unroll
+        for (int d = 4; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFu, v, d);
+        if (threadIdx.x == 0) atomicAdd(out, v);
+    }
+}
+
+int ba_launch_cost(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k, int mode,
+                   double *scalar_out, cudaStream_t st) {
+    if (P.n_obs_local > 0) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int want = (P.n_obs_local + 255) / 256;
+        const int grid = want < sms * 8 ? want : sms * 8;
+        k_cost<<<grid, 256, 0, st>>>(P, x, k, mode, scalar_out);
+        XRB_LAUNCHED();
+    }
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+__global__ void k_residuals(BAProblemDev P, BAStateDev x, BAConsts k,
+                            const int32_t *__restrict__ obs_orig, double *__restrict__ out) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= P.n_obs_local) return;
+    const int p = point_of_obs(P.pt_ptr, P.n_pts_local, o);
+    const int c = P.obs_cam[o], ii = P.cam_intr[c];
+    Obs e;
+    eval_obs<false>(x.q + 4 * (size_t)c, x.t + 3 * (size_t)c, x.X + 3 * (size_t)p, P.intr_model[ii],
+                    P.intr + 8 * (size_t)ii, P.obs_uv[2 * (size_t)o], P.obs_uv[2 * (size_t)o + 1], k, false, e);
+    const size_t dst = obs_orig[o];
+    out[2 * dst] = e.r0, out[2 * dst + 1] = e.r1;
+}
+
+int ba_launch_residuals(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
+                        const int32_t *obs_orig, double *out, cudaStream_t st) {
+    if (P.n_obs_local > 0) {
+        k_residuals<<<(P.n_obs_local + 255) / 256, 256, 0, st>>>(P, x, k, obs_orig, out);
+        XRB_LAUNCHED();
+    }
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+}  // namespace xrb

@@ -1,0 +1,96 @@
+// ba_kernels.cuh — device-side contract of the bundle-adjustment engine (path B).
+//
+// What runs where (one LM iteration = one pass through steps 2-5, TrustRegionMinimizer +
+// LevenbergMarquardtStrategy + SchurEliminator<2,3,3> semantics):
+//   1  k_colnorm        iteration 0 only: Jacobi column scaling 1/(1+||J_col||)
+//   2  k_schur          fused residual + Jacobian + Huber + block Hessians + Schur
+//                       complement: builds the reduced camera system S, rhs (point-major,
+//                       one warp per point, FP64 atomics into L2-resident S)
+//   3  k_cam_diag + chol_* (ba_chol.cu)  S += U + D^2, blocked FP64 Cholesky, solve
+//   4  k_backsub + k_cam_update          point steps, candidate state, model cost change
+//   5  k_cost           cost at the candidate
+// Reference entry points replaced: ceres::Solve at ba_solver.cc:591,636,672 for problems
+// built by BASolver::SetUp (ba_solver.cc:330-356) from ReProjectionCost
+// (cost_factor_ceres.h:19-40) and the camera models (camera_model.hpp:93-210).
+#pragma once
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace xrb {
+
+struct BAConsts {  // cost-functor / loss constants (xrb_ba_options)
+    double huber_a, huber_b;  // a, a^2
+    double min_depth, neg_depth_residual;
+};
+
+// Read-only problem description on the device (point-major CSR).
+struct BAProblemDev {
+    int n_cams, n_pts_local, n_obs_local, nc;  // nc = reduced camera-system dimension
+    const double *intr;                         // [8 * n_intr]
+    const int32_t *intr_model;                  // [n_intr]
+    const int32_t *cam_intr;                    // [n_cams]
+    const int32_t *colq, *colt;                 // [n_cams] first reduced column or -1
+    const int32_t *pt_ptr;                      // [n_pts_local + 1]
+    const int32_t *obs_cam;                     // [n_obs_local] (point-major order)
+    const double *obs_uv;                       // [2 * n_obs_local]
+    const uint8_t *pt_var;                      // [n_pts_local]
+};
+
+// Mutable state: a set of (q, t, X) arrays.
+struct BAStateDev {
+    double *q, *t, *X;  // [4C], [3C], [3 * n_pts_local]
+};
+
+// Exchange buffer layout (one SUM all-reduce per linear solve in multi-GPU mode):
+//   S    : (nc + 1) x ld   lower triangle of the reduced camera system, row nc = rhs^T
+//   U    : nc x 6          rows of the camera block-diagonal J_c^T J_c
+//   gc   : nc              J_c^T r (scaled), for the gradient norm
+//   n2c  : nc              squared column norms (iteration 0 only)
+struct BALinSys {
+    double *S;
+    int ld;
+    double *U, *gc, *n2c;
+    double *Vinv, *gp;  // per local point: V^-1 (6), g_p (3)
+    double *sc, *sp;    // Jacobi scaling: camera columns [nc], point columns [3 * n_pts_local]
+};
+
+// scalar slots (doubles) produced on the device, read by the host controller
+enum {
+    SC_MODEL_CHANGE = 0,  // -(J s)^T (r + J s / 2)
+    SC_CAND_COST = 1,
+    SC_STEP_NORM2 = 2,    // ||x - x_candidate||^2 (ambient)
+    SC_XNORM2 = 3,        // ||x_candidate||^2 over variable blocks
+    SC_COST = 4,          // cost at the current state (iteration 0 / fixed cost)
+    SC_GRAD_MAX_PT = 5,   // max |g_p / scale| over local variable points (as double bits)
+    SC_GRAD_MAX_CAM = 6,
+    SC_FAIL = 7,          // != 0: singular point block / non-finite value
+    SC_COUNT = 8
+};
+
+int ba_launch_colnorm(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
+                      const BALinSys &L, cudaStream_t st);
+int ba_launch_finish_scaling(const BAProblemDev &P, const BALinSys &L, cudaStream_t st);
+int ba_launch_schur(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
+                    const BALinSys &L, double inv_radius, double *scalars, cudaStream_t st);
+int ba_launch_cam_diag(const BAProblemDev &P, const BAStateDev &x, const BALinSys &L,
+                       double inv_radius, double *scalars, cudaStream_t st);
+int ba_launch_backsub(const BAProblemDev &P, const BAStateDev &x, const BAStateDev &cand,
+                      const BAConsts &k, const BALinSys &L, const double *yc, double *step_p,
+                      double *scalars, cudaStream_t st);
+int ba_launch_cam_update(const BAProblemDev &P, const BAStateDev &x, const BAStateDev &cand,
+                         const BALinSys &L, const double *yc, double *scalars, int add_norms,
+                         cudaStream_t st);
+// mode 0: active residual blocks (>=1 variable block); mode 1: all-constant blocks (fixed cost)
+int ba_launch_cost(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k, int mode,
+                   double *scalar_out, cudaStream_t st);
+int ba_launch_residuals(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
+                        const int32_t *obs_orig, double *out, cudaStream_t st);
+
+// ba_chol.cu — blocked FP64 Cholesky of S (n x n, leading dimension ld, row n = rhs) limited
+// to half-bandwidth bw, forward solve folded in (augmented row), blocked backward solve.
+// linv: scratch for the inverted diagonal blocks, ceil(n/64) * 64*64 doubles.
+int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, double *x_out,
+                             double *fail_flag, cudaStream_t st, int64_t *launches);
+
+}  // namespace xrb

@@ -32,10 +32,20 @@ struct Top2State {
 };
 
 // tie_rank orders equal dots the way the reference's scans do.
-//  rows   (RowMatch_Kernel, ProgramCU.cu:1798-1826): lane = j % 32 first, then j
+//  rows   (RowMatch_Kernel, ProgramCU.cu:1798-1826): each of 32 lanes keeps its first
+//         maximum (lowest j in the lane); the 16/8/4/2/1 tree then keeps the LOWER tree
+//         position on ties, which ranks lanes in bit-reversed order (0,16,8,24,4,20,...):
+//         rank = (bitrev5(j % 32), j / 32).
 //  columns(MultiplyDescriptor partials + ColMatch, :1556-1570,1858-1864): lowest i
-__host__ __device__ inline uint32_t row_tie_rank(uint32_t j) { return ((j & 31u) << 20) | (j >> 5); }
-__host__ __device__ inline uint32_t row_tie_unrank(uint32_t r) { return ((r & 0xFFFFFu) << 5) | (r >> 20); }
+__host__ __device__ inline uint32_t bitrev5(uint32_t x) {
+    return ((x & 1u) << 4) | ((x & 2u) << 2) | (x & 4u) | ((x & 8u) >> 2) | ((x & 16u) >> 4);
+}
+__host__ __device__ inline uint32_t row_tie_rank(uint32_t j) {
+    return (bitrev5(j & 31u) << 20) | (j >> 5);
+}
+__host__ __device__ inline uint32_t row_tie_unrank(uint32_t r) {
+    return ((r & 0xFFFFFu) << 5) | bitrev5(r >> 20);
+}
 
 int launch_vlow(float distmax, float ratiomax, int *vlow_dev, cudaStream_t st);
 
