@@ -63,12 +63,18 @@ int ensure_scratch(xrb_matcher *m, int n_pairs_hint) {
 }
 
 int score(xrb_matcher *m, const PairDesc *pd_dev, int n, int max_n1, int max_n2,
-          cudaStream_t st) {
+          cudaStream_t st, bool slots = false) {
     Top2State rows{m->rows_best.as<unsigned long long>(), m->rows_second.as<unsigned int>()};
     Top2State cols{m->cols_best.as<unsigned long long>(), m->cols_second.as<unsigned int>()};
-    if (m->variant == 2)
-        return launch_score_tc(pd_dev, n, max_n1, max_n2, m->state_stride, rows, cols,
-                               m->vlow.as<int>(), st);
+    if (m->variant == 2) {
+        if (slots)
+            return launch_score_tc(pd_dev, n, m->slot[0].as<uint8_t>(), (uint64_t)m->max_features,
+                                   m->slot[1].as<uint8_t>(), (uint64_t)m->max_features,
+                                   m->state_stride, rows, cols, m->vlow.as<int>(), st);
+        const uint64_t total = (uint64_t)m->offsets[m->n_images];
+        return launch_score_tc(pd_dev, n, m->block, total, m->block, total, m->state_stride, rows,
+                               cols, m->vlow.as<int>(), st);
+    }
     return launch_score_dp4a(pd_dev, n, max_n1, max_n2, m->state_stride, rows, cols,
                              m->vlow.as<int>(), st);
 }
@@ -166,7 +172,7 @@ int xrb_match_get(xrb_matcher *m, int max_match, uint32_t (*match_buffer)[2], fl
         cudaSuccess)
         return -1;
     if (launch_vlow(distmax, ratiomax, m->vlow.as<int>(), st)) return -1;
-    if (score(m, m->pairdesc.as<PairDesc>(), 1, n1, n2, st)) return -1;
+    if (score(m, m->pairdesc.as<PairDesc>(), 1, n1, n2, st, true)) return -1;
     if (finalize(m, m->pairdesc.as<PairDesc>(), 1, distmax, ratiomax, mutual_best_match,
                  max_match, m->counts.as<int32_t>(), m->strided.as<uint32_t[2]>(), stride, st))
         return -1;

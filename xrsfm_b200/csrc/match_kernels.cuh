@@ -55,9 +55,11 @@ int launch_score_dp4a(const PairDesc *pairs_dev, int n_pairs, int max_n1, int ma
                       cudaStream_t st);
 
 // Generation 2: tcgen05 int8 MMA, accumulators in TMEM (match_tc.cu).
-int launch_score_tc(const PairDesc *pairs_dev, int n_pairs, int max_n1, int max_n2,
-                    int state_stride, Top2State rows, Top2State cols, const int *vlow_dev,
-                    cudaStream_t st);
+// baseA/baseB: device blocks every PairDesc::a / ::b points into (rowsA/rowsB descriptors);
+// the TMA tensor maps are built over them.
+int launch_score_tc(const PairDesc *pairs_dev, int n_pairs, const uint8_t *baseA, uint64_t rowsA,
+                    const uint8_t *baseB, uint64_t rowsB, int state_stride, Top2State rows,
+                    Top2State cols, const int *vlow_dev, cudaStream_t st);
 bool score_tc_available();
 
 int launch_finalize(const PairDesc *pairs_dev, int n_pairs, int state_stride, Top2State rows,
