@@ -85,6 +85,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores():
+    """CPU threads this process may really use: affinity mask and cgroup quota, not the
+    box's core count (the GPU box reports 128 cores but runs jobs under a quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 
@@ -243,7 +256,7 @@ def cpu_baseline_ba(args, sample_iters=2):
     host cores, same C2 scene, bounded sample of LM iterations."""
     from tests import oracle_lib as ol
     sc = make_c2(args.scale)
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     t0 = time.perf_counter()
     s = ol.ba_solve(sc, ol.ba_options(max_iterations=sample_iters, fixed_iterations=1, **GBA_ACCURATE), cores)
     dt = time.perf_counter() - t0
@@ -360,7 +373,7 @@ def cpu_baseline_match(n_feat=4096, seconds=12.0):
     from tests import oracle_lib as ol
     from xrsfm_b200 import synth
     imgs, _ = synth.make_images(4, n_feat, seed=3)
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     n, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < seconds:
         ol.match_pair(imgs[n % 3], imgs[n % 3 + 1])
@@ -398,7 +411,7 @@ def reference_arm(args, rank, world):
         return None
     from tests import oracle_lib as ol
     sc = make_c2(args.scale)
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     steps = max(1, min(args.steps, 4))  # bounded sample: ~2-3 s per LM iteration on 8 cores
     warm = sc.copy_state()
     ol.ba_solve(warm, ol.ba_options(max_iterations=min(1, args.warmup), fixed_iterations=1, **GBA_ACCURATE), cores)

@@ -207,6 +207,12 @@ typedef int (*xrb_allreduce_fn)(void *buf_dev, size_t count, void *user);
 int xrb_ba_set_exchange(xrb_ba_solver *s, int rank, int world, xrb_allreduce_fn fn,
                         void *user);
 
+/* Host-only helper (needs no GPU): the contiguous point range [*lo, *hi) rank `rank` of
+ * `world` owns, given the number of observations of every point.  Shards are balanced by
+ * the Schur-complement work sum_p (k_p^2 + 4 k_p).  xrb_ba_load uses exactly this split. */
+int xrb_ba_shard_range(int32_t n_pts, const int32_t *obs_per_point, int rank, int world,
+                       int32_t *lo, int32_t *hi);
+
 /* Replaces ceres::Solve at ba_solver.cc:591,636,672 (problem build included): HOST
  * arrays in, poses/points updated in place, summary filled.  In multi-GPU mode every
  * rank passes the FULL problem and the solver keeps only its shard of the points

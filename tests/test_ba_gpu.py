@@ -45,9 +45,12 @@ def _compare_logs(s_got, s_ref, rel=1e-7):
         assert a.step_is_successful == b.step_is_successful, i
         assert a.cost == pytest.approx(b.cost, rel=rel), i
         assert a.trust_region_radius == pytest.approx(b.trust_region_radius, rel=1e-5), i
-        assert a.model_cost_change == pytest.approx(b.model_cost_change, rel=1e-5, abs=1e-9), i
-        assert a.step_norm == pytest.approx(b.step_norm, rel=1e-5, abs=1e-12), i
-        assert a.gradient_max_norm == pytest.approx(b.gradient_max_norm, rel=1e-5, abs=1e-9), i
+        # derived quantities shrink towards convergence and pick up the round-off of the
+        # earlier iterations: compare them 100x looser than the costs
+        loose = max(1e-5, 100 * rel)
+        assert a.model_cost_change == pytest.approx(b.model_cost_change, rel=loose, abs=1e-9), i
+        assert a.step_norm == pytest.approx(b.step_norm, rel=loose, abs=1e-12), i
+        assert a.gradient_max_norm == pytest.approx(b.gradient_max_norm, rel=loose, abs=1e-9), i
 
 
 def test_c1_single_iteration(solver):

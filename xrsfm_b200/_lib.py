@@ -84,6 +84,7 @@ SIGNATURES = {
     "xrb_ba_create": (C.c_void_p, [C.c_int]),
     "xrb_ba_destroy": (None, [C.c_void_p]),
     "xrb_ba_set_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p]),
+    "xrb_ba_shard_range": (C.c_int, [C.c_int32, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "xrb_ba_solve": (C.c_int, [C.c_void_p, C.POINTER(BAProblem), C.POINTER(BAOptions),
                                C.POINTER(BASummary)]),
     "xrb_ba_load": (C.c_int, [C.c_void_p, C.POINTER(BAProblem)]),

@@ -173,21 +173,14 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
     }
     s->bw = std::max(bw, 5);
 
-    // ---- shard the points over ranks, balanced by the Schur work sum k_p^2 + k_p
+    // ---- shard the points over ranks, balanced by the Schur work (xrb_ba_shard_range)
     int p_lo = 0, p_hi = NP;
     if (s->world > 1) {
-        std::vector<double> w(NP + 1, 0.0);
-        for (int p = 0; p < NP; ++p) {
-            const double k = pt_ptr[p + 1] - pt_ptr[p];
-            w[p + 1] = w[p] + k * k + 4.0 * k;
-        }
-        auto cut = [&](int r) {
-            const double target = w[NP] * r / s->world;
-            return (int)(std::lower_bound(w.begin(), w.end(), target) - w.begin());
-        };
-        p_lo = std::min(NP, cut(s->rank)), p_hi = s->rank + 1 == s->world ? NP : std::min(NP, cut(s->rank + 1));
-        if (s->rank == 0) p_lo = 0;
-        p_hi = std::max(p_hi, p_lo);
+        std::vector<int32_t> kp(NP);
+        for (int p = 0; p < NP; ++p) kp[p] = pt_ptr[p + 1] - pt_ptr[p];
+        int32_t lo32 = 0, hi32 = NP;
+        xrb_ba_shard_range(NP, kp.data(), s->rank, s->world, &lo32, &hi32);
+        p_lo = lo32, p_hi = hi32;
     }
     s->p_lo = p_lo, s->P_local = p_hi - p_lo;
     const int o_lo = pt_ptr[p_lo], o_hi = pt_ptr[p_hi];
@@ -532,6 +525,28 @@ void xrb_ba_default_options(xrb_ba_options *o) {
     o->neg_depth_residual = 12.0;  // cost_factor_ceres.h:31
     o->verbose = 0;
     o->fixed_iterations = 0;
+}
+
+int xrb_ba_shard_range(int32_t n_pts, const int32_t *obs_per_point, int rank, int world, int32_t *lo,
+                       int32_t *hi) {
+    if (n_pts < 0 || world < 1 || rank < 0 || rank >= world || !lo || !hi || (n_pts && !obs_per_point)) {
+        set_error("ba_shard_range: bad arguments");
+        return XRB_ERR_INVALID;
+    }
+    std::vector<double> w((size_t)n_pts + 1, 0.0);
+    for (int p = 0; p < n_pts; ++p) {
+        const double k = obs_per_point[p];
+        w[p + 1] = w[p] + k * k + 4.0 * k;
+    }
+    auto cut = [&](int r) {
+        if (r <= 0) return 0;
+        if (r >= world) return (int)n_pts;
+        const double target = w[n_pts] * r / world;
+        return (int)(std::lower_bound(w.begin(), w.end(), target) - w.begin());
+    };
+    *lo = std::min<int>(n_pts, cut(rank));
+    *hi = std::max<int>(*lo, std::min<int>(n_pts, cut(rank + 1)));
+    return XRB_OK;
 }
 
 xrb_ba_solver *xrb_ba_create(int device) {
