@@ -114,7 +114,9 @@ int xrb_match_pairs_device(xrb_matcher *m, int n_pairs, const int32_t (*pairs_de
 int xrb_match_debug_dist_table(float *out_host, int n);
 
 /* Which kernel generation a matcher runs: 0 = auto (best available), 1 = dp4a tiles,
- * 2 = tcgen05.  Returns the variant now in force. */
+ * 2 = tcgen05 + global top-2 state, 3 = tcgen05 with the pair's state in shared memory and
+ * the finalize step fused in (falls back to 2 for images above 4096 descriptors).
+ * Returns the variant now in force. */
 int xrb_match_set_variant(xrb_matcher *m, int variant);
 
 /* ------------------------------------------------------------------ */

@@ -13,7 +13,7 @@ from xrsfm_b200 import _lib, matching, synth
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [1, 2]
+VARIANTS = [1, 2, 3]
 
 
 @pytest.fixture(scope="module")

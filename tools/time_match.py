@@ -24,19 +24,19 @@ pd = torch.from_numpy(pairs).cuda()
 counts = torch.zeros(pairs.shape[0], dtype=torch.int32, device="cuda")
 out = torch.zeros((pairs.shape[0], n_feat, 2), dtype=torch.int32, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
-for variant in (1, 2):
+for variant, distmax in ((1, 0.7), (2, 0.7), (2, 1e-3), (3, 0.7), (3, 1e-3)):  # distmax 1e-3: no candidates -> pure MMA + TMEM read + filter
     if m.set_variant(variant) != variant:
         continue
     for it in range(3):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record()
-        _lib.check(lib.xrb_match_pairs_device(m._h, pairs.shape[0], pd.data_ptr(), 0.7, 0.8, 1, 16384,
+        _lib.check(lib.xrb_match_pairs_device(m._h, pairs.shape[0], pd.data_ptr(), distmax, 0.8, 1, 16384,
                                               counts.data_ptr(), out.data_ptr(), n_feat, st), "pairs")
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        print(f"variant {variant}: {ms:.2f} ms for {pairs.shape[0]} pairs -> {pairs.shape[0] / ms * 1e3:.0f} pairs/s,"
+        print(f"variant {variant} distmax {distmax}: {ms:.2f} ms for {pairs.shape[0]} pairs -> {pairs.shape[0] / ms * 1e3:.0f} pairs/s,"
               f" mean matches {counts.float().mean().item():.0f}")
 if ol.load_ref() is not None:
     t = time.time()

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -46,6 +47,10 @@ struct xrb_ba_solver {
     // device: problem
     DevBuf d_intr, d_intr_model, d_cam_intr, d_colq, d_colt, d_pt_ptr, d_obs_cam, d_obs_uv,
         d_pt_var, d_obs_orig;
+    // generation-2 Schur structure (ba_struct.cu) and per-observation records
+    DevBuf d_obs_pt, d_cam_ptr, d_cam_obs, d_inc, d_blk_ptr, d_blk_cams, d_Tt, d_h;
+    int schur_gen = 2, n_blocks = 0;
+    int64_t n_inc = 0;
     // device: states
     DevBuf d_q[3], d_t[3], d_X[3];  // 0 = current, 1 = candidate, 2 = initial copy
     int cur = 0;
@@ -65,6 +70,9 @@ struct xrb_ba_solver {
         p.colq = d_colq.as<int32_t>(), p.colt = d_colt.as<int32_t>();
         p.pt_ptr = d_pt_ptr.as<int32_t>(), p.obs_cam = d_obs_cam.as<int32_t>();
         p.obs_uv = d_obs_uv.as<double>(), p.pt_var = d_pt_var.as<uint8_t>();
+        p.obs_pt = d_obs_pt.as<int32_t>(), p.cam_ptr = d_cam_ptr.as<int32_t>(), p.cam_obs = d_cam_obs.as<int32_t>();
+        p.n_blocks = schur_gen == 2 ? n_blocks : -1;
+        p.blk_ptr = d_blk_ptr.as<int32_t>(), p.blk_cams = d_blk_cams.as<int2>(), p.inc = d_inc.as<int2>();
         return p;
     }
     BAStateDev state(int i) const { return {d_q[i].as<double>(), d_t[i].as<double>(), d_X[i].as<double>()}; }
@@ -74,6 +82,7 @@ struct xrb_ba_solver {
         L.S = E, L.ld = ld, L.U = E + off_U, L.gc = E + off_gc, L.n2c = E + off_n2c;
         L.Vinv = d_Vinv.as<double>(), L.gp = d_gp.as<double>();
         L.sc = d_sc.as<double>(), L.sp = d_sp.as<double>();
+        L.Tt = d_Tt.as<double>(), L.h = d_h.as<double>();
         return L;
     }
     double *scalE() const { return d_E.as<double>() + off_scalE; }
@@ -212,6 +221,37 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
         if ((rc = upload(s->d_X[i], P->pts + 3 * (size_t)p_lo, 3 * (size_t)s->P_local, st))) return rc;
     }
     s->cur = 0;
+    // ---- generation-2 Schur structure: obs -> point, camera-major CSR, block incidence lists
+    {
+        const char *env = getenv("XRB_BA_SCHUR");
+        s->schur_gen = (env && atoi(env) == 1) ? 1 : 2;
+        std::vector<int32_t> l_pt(s->O_local), c_ptr(C + 1, 0), c_obs(s->O_local);
+        for (int p = 0; p < s->P_local; ++p)
+            for (int k = l_ptr[p]; k < l_ptr[p + 1]; ++k) l_pt[k] = p;
+        for (int k = 0; k < s->O_local; ++k) c_ptr[l_cam[k] + 1]++;
+        for (int c = 0; c < C; ++c) c_ptr[c + 1] += c_ptr[c];
+        {
+            std::vector<int32_t> cursor(c_ptr.begin(), c_ptr.end() - 1);
+            for (int k = 0; k < s->O_local; ++k) c_obs[cursor[l_cam[k]]++] = k;
+        }
+        if ((rc = upload(s->d_obs_pt, l_pt.data(), l_pt.size(), st))) return rc;
+        if ((rc = upload(s->d_cam_ptr, c_ptr.data(), c_ptr.size(), st))) return rc;
+        if ((rc = upload(s->d_cam_obs, c_obs.data(), c_obs.size(), st))) return rc;
+        s->n_blocks = 0, s->n_inc = 0;
+        if (s->schur_gen == 2) {
+            std::vector<int64_t> pair_ptr(s->P_local + 1, 0);
+            for (int p = 0; p < s->P_local; ++p) {
+                const int64_t k = l_ptr[p + 1] - l_ptr[p];
+                pair_ptr[p + 1] = pair_ptr[p] + k * (k - 1) / 2;
+            }
+            if ((rc = s->d_Tt.reserve(std::max<size_t>(1, 18 * (size_t)s->O_local) * 8))) return rc;
+            if ((rc = s->d_h.reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
+            BAProblemDev pd = s->prob();
+            pd.nc = s->nc;
+            if ((rc = ba_build_block_lists(pd, pair_ptr, s->d_inc, s->d_blk_ptr, s->d_blk_cams, &s->n_blocks, &s->n_inc, st)))
+                return rc;
+        }
+    }
     // ---- linear-system storage
     const int nc = s->nc;
     s->ld = ((nc + 1 + 7) / 8) * 8;
@@ -256,8 +296,15 @@ int compute_step(xrb_ba_solver *s, const BAConsts &k, double radius, cudaStream_
     XRB_CUDA(cudaMemsetAsync(s->d_E.p, 0, s->off_n2c * 8, st));
     XRB_CUDA(cudaMemsetAsync(s->scalE(), 0, (SC_COUNT + s->world) * 8, st));
     XRB_CUDA(cudaMemsetAsync(s->d_scal.p, 0, 2 * SC_COUNT * 8, st));
-    if ((rc = ba_launch_schur(P, x, k, L, inv_radius, s->scalE(), st))) return rc;
-    s->launches[0]++;
+    if (s->schur_gen == 2) {
+        if ((rc = ba_launch_lin(P, x, k, L, inv_radius, s->scalE(), st))) return rc;
+        if ((rc = ba_launch_gather(P, L, st))) return rc;
+        if ((rc = ba_launch_cam_blocks(P, x, k, L, st))) return rc;
+        s->launches[0] += 3;
+    } else {
+        if ((rc = ba_launch_schur(P, x, k, L, inv_radius, s->scalE(), st))) return rc;
+        s->launches[0]++;
+    }
     ev[1].rec(st);
     if (s->world > 1) {
         XRB_CUDA(cudaMemcpyAsync(s->slots() + s->rank, s->scalE() + SC_GRAD_MAX_PT, 8, cudaMemcpyDeviceToDevice, st));
@@ -567,7 +614,9 @@ void xrb_ba_destroy(xrb_ba_solver *s) {
     cudaStreamSynchronize(s->own_stream);
     DevBuf *bufs[] = {&s->d_intr, &s->d_intr_model, &s->d_cam_intr, &s->d_colq, &s->d_colt, &s->d_pt_ptr,
                       &s->d_obs_cam, &s->d_obs_uv, &s->d_pt_var, &s->d_obs_orig, &s->d_E, &s->d_Vinv, &s->d_gp,
-                      &s->d_sc, &s->d_sp, &s->d_linv, &s->d_yc, &s->d_step_p, &s->d_scal, &s->d_full};
+                      &s->d_sc, &s->d_sp, &s->d_linv, &s->d_yc, &s->d_step_p, &s->d_scal, &s->d_full,
+                      &s->d_obs_pt, &s->d_cam_ptr, &s->d_cam_obs, &s->d_inc, &s->d_blk_ptr, &s->d_blk_cams,
+                      &s->d_Tt, &s->d_h};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 3; ++i) s->d_q[i].release(), s->d_t[i].release(), s->d_X[i].release();
     if (s->h_scal) cudaFreeHost(s->h_scal);

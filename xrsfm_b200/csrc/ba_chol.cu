@@ -3,211 +3,249 @@
 // (the right-hand side rides along as row n of the matrix), blocked backward substitution.
 //
 // Replaces Ceres' SparseSchurComplementSolver factor+solve (selected by ba_solver.cc:74).
-// Generation 1: 64x64 FP64 FMA tiles staged in shared memory; see DESIGN.md §B.4 for the
-// roofline (FP64 pipe) and the planned DMMA variant.
+// Right-looking, block size 64:
+//   chol_diag    one CTA: L_kk = chol(A_kk) and its inverse, both in shared memory
+//   chol_panel   L_ik = A_ik Linv_kk^T   — FP64 GEMM tiles (128 x 64 x 64)
+//   chol_update  A_ij -= L_ik L_jk^T     — FP64 GEMM tiles (128 x 128 x 64 or 64 x 64 x 64),
+//                lower-triangular tile pairs inside the band; this is where the n^3/3 flops are
+//   chol_backsolve  one launch per block column, bottom-up
+// The whole launch sequence is fixed for a given (n, bandwidth) and is replayed as a CUDA
+// graph.  Roofline: FP64 FMA pipe (64 FMA/clk/SM); see DESIGN.md §B.4.
 #include <cuda_runtime.h>
+
+#include <map>
+#include <tuple>
 
 #include "ba_kernels.cuh"
 
 namespace xrb {
 
-constexpr int NB = 64;        // block size
-constexpr int TLD = NB + 2;   // shared tile leading dimension (doubles)
+constexpr int NB = 64;  // block-column width == GEMM depth
+constexpr int kDiagSmem = (2 * NB * (NB + 1) + NB) * (int)sizeof(double);
 
-// ---- 1. diagonal block: L_kk = chol(A_kk) in place, Linv = L_kk^-1 -------------------------
+// ---- 1. diagonal block ---------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 chol_diag(double *__restrict__ S, int ld, int k0, int kb, double *__restrict__ linv_out,
           double *__restrict__ fail) {
     extern __shared__ __align__(16) double smem_d[];
-    double(*A)[TLD] = reinterpret_cast<double(*)[TLD]>(smem_d);
-    double(*Li)[TLD] = reinterpret_cast<double(*)[TLD]>(smem_d + NB * TLD);
+    double(*A)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d);
+    double(*Li)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d + NB * (NB + 1));
+    double *Ld = smem_d + 2 * NB * (NB + 1);
     const int tid = threadIdx.x;
     for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int r = idx / NB, c = idx % NB;
+        const int r = idx >> 6, c = idx & 63;
         A[r][c] = (r < kb && c <= r) ? S[(size_t)(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
         Li[r][c] = 0.0;
     }
     __syncthreads();
+    const int r = tid >> 2, sub = tid & 3;
     for (int j = 0; j < kb; ++j) {
-        if (tid == 0) {
-            double d = A[j][j];
-            if (!(d > 0.0) || !isfinite(d)) {
-                *fail = 1.0;
-                d = 1.0;
-            }
-            A[j][j] = sqrt(d);
+        double d = A[j][j];
+        if (!(d > 0.0) || !isfinite(d)) {
+            if (tid == 0) *fail = 1.0;
+            d = 1.0;
         }
+        const double l = sqrt(d), inv = 1.0 / l;
+        if (tid == j) Ld[j] = l;
+        if (tid > j && tid < kb) A[tid][j] *= inv;
         __syncthreads();
-        const double inv = 1.0 / A[j][j];
-        for (int i = j + 1 + tid; i < kb; i += 256) A[i][j] *= inv;
-        __syncthreads();
-        // rank-1 update of the trailing lower triangle
-        const int m = kb - j - 1;
-        for (int idx = tid; idx < m * m; idx += 256) {
-            const int r = j + 1 + idx / m, c = j + 1 + idx % m;
-            if (c <= r) A[r][c] -= A[r][j] * A[c][j];
+        if (r > j && r < kb) {
+            const double arj = A[r][j];
+            for (int c = j + 1 + sub; c <= r; c += 4) A[r][c] -= arj * A[c][j];
         }
         __syncthreads();
     }
-    // inverse of the lower-triangular block: column c of Linv by forward substitution
-    if (tid < kb) {
-        const int c = tid;
-        for (int r = c; r < kb; ++r) {
-            double v = (r == c) ? 1.0 : 0.0;
-            for (int p = c; p < r; ++p) v -= A[r][p] * Li[p][c];
-            Li[r][c] = v / A[r][r];
+    if (tid < kb) A[tid][tid] = Ld[tid];
+    __syncthreads();
+    // Linv = L^-1: column c by forward substitution, 4 lanes share the inner products
+    {
+        const int c = tid >> 2;  // 64 columns x 4 lanes; every lane walks all rows (shuffles
+        for (int rr = 0; rr < kb; ++rr) {  // need the whole warp), rows above the diagonal idle
+            double v = 0.0;
+            if (rr >= c)
+                for (int p = c + sub; p < rr; p += 4) v += A[rr][p] * Li[p][c];
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+            if (sub == 0 && c < kb && rr >= c) Li[rr][c] = ((rr == c ? 1.0 : 0.0) - v) / A[rr][rr];
+            __syncwarp();
         }
     }
     __syncthreads();
     for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int r = idx / NB, c = idx % NB;
-        if (r < kb && c <= r) S[(size_t)(k0 + r) * ld + k0 + c] = A[r][c];
-        linv_out[idx] = (r < kb && c < kb) ? Li[r][c] : 0.0;
+        const int rr = idx >> 6, c = idx & 63;
+        if (rr < kb && c <= rr) S[(size_t)(k0 + rr) * ld + k0 + c] = A[rr][c];
+        linv_out[idx] = (rr < kb && c < kb) ? Li[rr][c] : 0.0;
     }
 }
 
-// 64x64x64 FP64 tile product helper: acc[4][4] += sum_p At[p][row] * Bt[p][col]
-// (both operands stored p-major so a thread's 4 rows / 4 cols are contiguous).
-__device__ __forceinline__ void tile_mma(double (*At)[TLD], double (*Bt)[TLD], int ty,
-                                         int tx, double acc[4][4], int kb) {
-#pragma unroll 4
-    for (int p = 0; p < kb; ++p) {
-        double a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = At[p][ty * 4 + i], b[i] = Bt[p][tx * 4 + i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
-    }
-}
+// ---- FP64 GEMM tile: acc[i][j] = sum_p X[row(ty,i)][p] * Y[col(tx,j)][p], p < 64 -------------
+// 256 threads as 16 x 16; thread (ty, tx) owns rows ty + 16 i and columns tx + 16 j, so that
+// for a fixed p the 16 tx lanes read 16 consecutive doubles (one shared-memory wavefront) and
+// the two ty values of a warp read two adjacent doubles (broadcast).  Operands are staged
+// p-major: Xs[p][row], Ys[p][col].
+template <int TM, int TN>
+struct Tile {
+    static constexpr int RM = TM / 16, RN = TN / 16;
+    static constexpr int LDX = TM + 1, LDY = TN + 1;
+    static constexpr int kSmemBytes = NB * (LDX + LDY) * (int)sizeof(double);
 
-// ---- 2. panel: L_ik = A_ik * Linv^T for the rows below the diagonal block -------------------
-// row_list semantics: tile t covers rows r0 + 64 t ... ; the last tile of the launch is the
-// single right-hand-side row n when it lies outside the band.
+    // global row-major [row][p] -> shared [p][row]; rows >= nrows and p >= kb are zero
+    template <int T>
+    __device__ static void stage(double *dst, int ldd, const double *__restrict__ src, size_t ld, int nrows,
+                                 int kb) {
+        for (int idx = threadIdx.x; idx < T * (NB / 2); idx += 256) {
+            const int row = idx >> 5, p = (idx & 31) * 2;
+            double2 v = make_double2(0.0, 0.0);
+            if (row < nrows) {
+                const double *g = src + (size_t)row * ld + p;
+                if (p + 1 < kb)
+                    v = *reinterpret_cast<const double2 *>(g);
+                else if (p < kb)
+                    v.x = g[0];
+            }
+            dst[p * ldd + row] = v.x;
+            dst[(p + 1) * ldd + row] = v.y;
+        }
+    }
+
+    __device__ static void mma(const double *Xs, const double *Ys, double (&acc)[RM][RN]) {
+        const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll 2
+        for (int p = 0; p < NB; ++p) {
+            double a[RM], b[RN];
+#pragma unroll
+            for (int i = 0; i < RM; ++i) a[i] = Xs[p * LDX + ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < RN; ++j) b[j] = Ys[p * LDY + tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+#pragma unroll
+                for (int j = 0; j < RN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+    }
+};
+
+// ---- 2. panel: L_ik = A_ik * Linv^T ----------------------------------------------------------
+// The source block column must be 16-byte aligned for the double2 loads: ld % 2 == 0 and
+// k0 % 2 == 0 hold by construction (ld is a multiple of 8, k0 a multiple of 64).
 __global__ void __launch_bounds__(256)
 chol_panel(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int rhs_row,
            const double *__restrict__ linv) {
+    using T = Tile<128, 64>;
     extern __shared__ __align__(16) double smem_d[];
-    double(*At)[TLD] = reinterpret_cast<double(*)[TLD]>(smem_d);             // At[p][i] = A[row i][k0+p]
-    double(*Bt)[TLD] = reinterpret_cast<double(*)[TLD]>(smem_d + NB * TLD);  // Bt[p][j] = Linv[j][p]
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    int row0 = r0 + blockIdx.x * NB;
-    int nrows = min(NB, r1 - row0);
-    if (row0 >= r1) {  // extra block: the rhs row alone
-        row0 = rhs_row;
-        nrows = 1;
-    }
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int i = idx / NB, p = idx % NB;
-        At[p][i] = (i < nrows && p < kb) ? S[(size_t)(row0 + i) * ld + k0 + p] : 0.0;
-        Bt[p][i] = linv[i * NB + p];  // Linv[j=i][p]
-    }
+    double *Xs = smem_d, *Ys = smem_d + NB * T::LDX;
+    int row0 = r0 + blockIdx.x * 128;
+    int nrows = min(128, r1 - row0);
+    if (row0 >= r1) row0 = rhs_row, nrows = 1;  // extra CTA: the right-hand-side row alone
+    T::stage<128>(Xs, T::LDX, S + (size_t)row0 * ld + k0, (size_t)ld, nrows, kb);
+    T::stage<64>(Ys, T::LDY, linv, (size_t)NB, NB, NB);  // Ys[p][j] = Linv[j][p]
     __syncthreads();
-    double acc[4][4] = {};
-    tile_mma(At, Bt, ty, tx, acc, kb);
+    double acc[T::RM][T::RN] = {};
+    T::mma(Xs, Ys, acc);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < T::RM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = ty * 4 + i, c = tx * 4 + j;
+        for (int j = 0; j < T::RN; ++j) {
+            const int r = ty + 16 * i, c = tx + 16 * j;
             if (r < nrows && c < kb) S[(size_t)(row0 + r) * ld + k0 + c] = acc[i][j];
         }
 }
 
-// ---- 3. trailing update: A_ij -= L_ik L_jk^T for tiles j <= i inside the band ---------------
+// ---- 3. trailing update: A_ij -= L_ik L_jk^T for tiles j <= i inside the band ----------------
+template <int TT>
 __global__ void __launch_bounds__(256)
 chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int rhs_row) {
+    using T = Tile<TT, TT>;
     extern __shared__ __align__(16) double smem_d[];
-    double(*At)[TLD] = reinterpret_cast<double(*)[TLD]>(smem_d);
-    double(*Bt)[TLD] = reinterpret_cast<double(*)[TLD]>(smem_d + NB * TLD);
-    const int ntile = (r1 - r0 + NB - 1) / NB;
-    int ti = blockIdx.y, tj = blockIdx.x;
+    double *Xs = smem_d, *Ys = smem_d + NB * T::LDX;
+    const int ntile = (r1 - r0 + TT - 1) / TT;
+    const int ti = blockIdx.y, tj = blockIdx.x;
     int row0, nrows;
     if (ti < ntile) {
         if (tj > ti) return;
-        row0 = r0 + ti * NB;
-        nrows = min(NB, r1 - row0);
-    } else {  // rhs row against every column tile
-        row0 = rhs_row;
-        nrows = 1;
+        row0 = r0 + ti * TT, nrows = min(TT, r1 - row0);
+    } else {
+        row0 = rhs_row, nrows = 1;  // right-hand-side row against every column tile
     }
     if (tj >= ntile) return;
-    const int col0 = r0 + tj * NB, ncols = min(NB, r1 - col0);
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int i = idx / NB, p = idx % NB;
-        At[p][i] = (i < nrows && p < kb) ? S[(size_t)(row0 + i) * ld + k0 + p] : 0.0;
-        Bt[p][i] = (i < ncols && p < kb) ? S[(size_t)(col0 + i) * ld + k0 + p] : 0.0;
-    }
+    const int col0 = r0 + tj * TT, ncols = min(TT, r1 - col0);
+    T::template stage<TT>(Xs, T::LDX, S + (size_t)row0 * ld + k0, (size_t)ld, nrows, kb);
+    T::template stage<TT>(Ys, T::LDY, S + (size_t)col0 * ld + k0, (size_t)ld, ncols, kb);
     __syncthreads();
-    double acc[4][4] = {};
-    tile_mma(At, Bt, ty, tx, acc, kb);
+    double acc[T::RM][T::RN] = {};
+    T::mma(Xs, Ys, acc);
     const bool diag_tile = (ti < ntile) && (ti == tj);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < T::RM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = ty * 4 + i, c = tx * 4 + j;
+        for (int j = 0; j < T::RN; ++j) {
+            const int r = ty + 16 * i, c = tx + 16 * j;
             if (r < nrows && c < ncols && (!diag_tile || c <= r))
                 S[(size_t)(row0 + r) * ld + col0 + c] -= acc[i][j];
         }
 }
 
 // ---- 4. backward substitution L^T x = y, one block column per launch ------------------------
-// Every CTA recomputes x_k = Linv_k^T y_k (64x64, trivial) and then removes x_k's
+// Every CTA recomputes x_k = Linv_k^T y_k (64 x 64, trivial) and then removes x_k's
 // contribution from its slice of the earlier unknowns: y_j -= sum_r L[k0+r][j] x_k[r].
 __global__ void __launch_bounds__(256)
 chol_backsolve(const double *__restrict__ S, int ld, int k0, int kb, int j0,
                const double *__restrict__ linv, double *__restrict__ y, double *__restrict__ x_out) {
     __shared__ double xk[NB];
     const int tid = threadIdx.x;
-    if (tid < NB) {
+    {
+        // x_k[c] = sum_{r >= c} Linv[r][c] y[k0 + r]; 4 lanes per column
+        const int c = tid >> 2, sub = tid & 3;
         double v = 0.0;
-        if (tid < kb)
-            for (int r = tid; r < kb; ++r) v += linv[r * NB + tid] * y[k0 + r];  // Linv^T
-        xk[tid] = v;
+        if (c < kb)
+            for (int r = c + sub; r < kb; r += 4) v += linv[r * NB + c] * y[k0 + r];
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+        if (sub == 0) xk[c] = c < kb ? v : 0.0;
     }
     __syncthreads();
     if (blockIdx.x == 0 && tid < kb) x_out[k0 + tid] = xk[tid];
     const int j = j0 + blockIdx.x * 256 + tid;
     if (j < k0) {
         double acc = 0.0;
-        for (int r = 0; r < kb; ++r) acc += S[(size_t)(k0 + r) * ld + j] * xk[r];
+#pragma unroll 8
+        for (int r = 0; r < kb; ++r) acc = fma(S[(size_t)(k0 + r) * ld + j], xk[r], acc);
         y[j] -= acc;
     }
 }
 
-int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, double *x_out,
-                             double *fail_flag, cudaStream_t st, int64_t *launches) {
-    if (n <= 0) return XRB_OK;
-    constexpr int kSmem = 2 * NB * TLD * (int)sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        XRB_CUDA(cudaFuncSetAttribute(chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        XRB_CUDA(cudaFuncSetAttribute(chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        XRB_CUDA(cudaFuncSetAttribute(chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        attr_set = true;
-    }
+namespace {
+
+int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, double *fail_flag,
+                cudaStream_t st, int64_t *count) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int nblk = (n + NB - 1) / NB;
     int64_t nl = 0;
     for (int kblk = 0; kblk < nblk; ++kblk) {
         const int k0 = kblk * NB, kb = min(NB, n - k0);
         double *li = linv + (size_t)kblk * NB * NB;
-        chol_diag<<<1, 256, kSmem, st>>>(S, ld, k0, kb, li, fail_flag);
-        ++nl;
+        chol_diag<<<1, 256, kDiagSmem, st>>>(S, ld, k0, kb, li, fail_flag);
         const int r0 = k0 + kb;
         const int r1 = min(n, r0 + bw);  // rows that can be non-zero in this block column
-        const int ntile = (r1 - r0 + NB - 1) / NB;
-        // the rhs row n always participates (it is dense)
-        chol_panel<<<ntile + 1, 256, kSmem, st>>>(S, ld, k0, kb, r0, r1, n, li);
-        ++nl;
-        dim3 grid(ntile > 0 ? ntile : 1, ntile + 1);
-        chol_update<<<grid, 256, kSmem, st>>>(S, ld, k0, kb, r0, r1, n);
-        ++nl;
+        const int np = (r1 - r0 + 127) / 128;
+        chol_panel<<<np + 1, 256, Tile<128, 64>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n, li);
+        // tile size: 128 while that still fills the machine, 64 for the tail
+        const int nt128 = (r1 - r0 + 127) / 128;
+        if (nt128 * (nt128 + 1) / 2 >= sms) {
+            dim3 grid(nt128, nt128 + 1);
+            chol_update<128><<<grid, 256, Tile<128, 128>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n);
+        } else {
+            const int nt64 = (r1 - r0 + 63) / 64;
+            dim3 grid(nt64 > 0 ? nt64 : 1, nt64 + 1);
+            chol_update<64><<<grid, 256, Tile<64, 64>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n);
+        }
+        nl += 3;
     }
-    // y = row n of S; solve L^T x = y block by block from the bottom
-    double *y = S + (size_t)n * ld;
+    double *y = S + (size_t)n * ld;  // y = L^-1 rhs now sits in row n
     for (int kblk = nblk - 1; kblk >= 0; --kblk) {
         const int k0 = kblk * NB, kb = min(NB, n - k0);
         const int j0 = max(0, k0 - bw - NB);
@@ -216,9 +254,73 @@ int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, dou
         chol_backsolve<<<grid, 256, 0, st>>>(S, ld, k0, kb, j0, linv + (size_t)kblk * NB * NB, y, x_out);
         ++nl;
     }
+    *count = nl;
+    return cudaGetLastError() == cudaSuccess ? XRB_OK : XRB_ERR_CUDA;
+}
+
+struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+};
+using GraphKey = std::tuple<double *, int, int, int, double *, double *, double *>;
+std::map<GraphKey, GraphEntry> g_graphs;
+
+}  // namespace
+
+int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, double *x_out,
+                             double *fail_flag, cudaStream_t st, int64_t *launches) {
+    if (n <= 0) return XRB_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        XRB_CUDA(cudaFuncSetAttribute(chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
+        XRB_CUDA(cudaFuncSetAttribute(chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Tile<128, 64>::kSmemBytes));
+        XRB_CUDA(cudaFuncSetAttribute(chol_update<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Tile<128, 128>::kSmemBytes));
+        XRB_CUDA(cudaFuncSetAttribute(chol_update<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Tile<64, 64>::kSmemBytes));
+        attr_set = true;
+    }
+    // The launch sequence depends only on (n, ld, bw) and the buffers: replay it as a graph.
+    const GraphKey key{S, n, ld, bw, linv, x_out, fail_flag};
+    auto it = g_graphs.find(key);
+    if (it == g_graphs.end()) {
+        GraphEntry e;
+        cudaGraph_t graph = nullptr;
+        cudaStream_t cs = nullptr;
+        bool ok = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            const int rc = enqueue_all(S, n, ld, bw, linv, x_out, fail_flag, cs, &e.launches);
+            ok = cudaStreamEndCapture(cs, &graph) == cudaSuccess && rc == XRB_OK && graph != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&e.exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        if (cs) cudaStreamDestroy(cs);
+        if (!ok) {
+            cudaGetLastError();
+            e.exec = nullptr;
+        }
+        if (g_graphs.size() > 64) {  // bounded cache
+            for (auto &kv : g_graphs)
+                if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+            g_graphs.clear();
+        }
+        it = g_graphs.emplace(key, e).first;
+    }
+    int64_t nl = 0;
+    if (it->second.exec) {
+        XRB_CUDA(cudaGraphLaunch(it->second.exec, st));
+        nl = it->second.launches;
+    } else {
+        const int rc = enqueue_all(S, n, ld, bw, linv, x_out, fail_flag, st, &nl);
+        if (rc) {
+            set_error("cholesky launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return rc;
+        }
+    }
     g_launches.fetch_add((uint64_t)nl, std::memory_order_relaxed);
     if (launches) *launches += nl;
-    XRB_CUDA(cudaGetLastError());
     return XRB_OK;
 }
 

@@ -482,6 +482,278 @@ int ba_launch_schur(const BAProblemDev &P, const BAStateDev &x, const BAConsts &
 }
 
 // =====================================================================================
+// 2'. Generation 2 of the Schur complement: no atomics.
+//   k_lin         point-major, one warp per point: phases A and B as in k_schur, then ONE
+//                 18-double record per observation, Tt_i = W_i (V + D^2)^-1/2, plus per
+//                 point (V + D^2)^-1 and h = (V + D^2)^-1 g.        (streaming writes only)
+//   k_gather      8 lanes per off-diagonal block (a, b): S_ab = - sum_{p in ab} Tt_i Tt_j^T
+//                 over the precomputed incidence list (ba_struct.cu), plain stores.
+//   k_cam_blocks  one CTA per camera: U_c = sum Jc^T Jc, g_c = sum Jc^T r,
+//                 rhs_c = sum Jc^T (r - JX h), S_cc -= sum Tt_i Tt_i^T, block-reduced.
+// The result is deterministic (fixed summation order) and S is written exactly once.
+// =====================================================================================
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_lin(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L, double inv_radius, double *__restrict__ scalars) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    double gmax = 0.0;
+    for (int p = warp; p < P.n_pts_local; p += nwarps) {
+        const int k0 = P.pt_ptr[p], kn = P.pt_ptr[p + 1] - k0;
+        if (kn == 0) continue;
+        const bool pvar = P.pt_var[p] != 0;
+        const int nchunks = (kn + kChunk - 1) / kChunk;
+        double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+        LinObs lo;
+        lo.active = false;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int i = ch * kChunk + lane;
+            lo.active = false;
+            if (i < kn) lin_obs(P, x, k, L, k0 + i, p, pvar, lo);
+            if (lo.active) {
+                const double *J = lo.JX;
+                V[0] += J[0] * J[0] + J[3] * J[3], V[1] += J[0] * J[1] + J[3] * J[4];
+                V[2] += J[0] * J[2] + J[3] * J[5], V[3] += J[1] * J[1] + J[4] * J[4];
+                V[4] += J[1] * J[2] + J[4] * J[5], V[5] += J[2] * J[2] + J[5] * J[5];
+                g[0] += J[0] * lo.r0 + J[3] * lo.r1;
+                g[1] += J[1] * lo.r0 + J[4] * lo.r1;
+                g[2] += J[2] * lo.r0 + J[5] * lo.r1;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) V[j] = warp_sum(V[j]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) g[j] = warp_sum(g[j]);
+        // (V + D^2) = Lc Lc^T (3x3 Cholesky); Tt = W Lc^-T so that Tt_i Tt_j^T = W_i (V+D^2)^-1 W_j^T
+        double l00 = 1, l10 = 0, l11 = 1, l20 = 0, l21 = 0, l22 = 1;
+        if (pvar) {
+            const double a = V[0] + fmin(fmax(V[0], 1e-6), 1e32) * inv_radius;
+            const double d = V[3] + fmin(fmax(V[3], 1e-6), 1e32) * inv_radius;
+            const double f = V[5] + fmin(fmax(V[5], 1e-6), 1e32) * inv_radius;
+            const double b = V[1], c = V[2], e = V[4];
+            l00 = sqrt(a), l10 = b / l00, l20 = c / l00;
+            const double t11 = d - l10 * l10;
+            l11 = sqrt(t11), l21 = (e - l20 * l10) / l11;
+            const double t22 = f - l20 * l20 - l21 * l21;
+            l22 = sqrt(t22);
+            const bool bad = !(a > 0.0) || !(t11 > 0.0) || !(t22 > 0.0) || !isfinite(l22);
+            if (lane == 0) {
+                if (bad) scalars[SC_FAIL] = 1.0;
+                // inverse through the factor: Vi = Lc^-T Lc^-1
+                const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+                const double m10 = -l10 * i00 * i11, m21 = -l21 * i11 * i22;
+                const double m20 = (l10 * l21 - l20 * l11) * i00 * i11 * i22;  // (Lc^-1)[2][0]
+                double Vi[6];
+                Vi[0] = i00 * i00 + m10 * m10 + m20 * m20, Vi[1] = m10 * i11 + m20 * m21, Vi[2] = m20 * i22;
+                Vi[3] = i11 * i11 + m21 * m21, Vi[4] = m21 * i22, Vi[5] = i22 * i22;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) L.Vinv[6 * (size_t)p + j] = Vi[j];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) L.gp[3 * (size_t)p + j] = g[j];
+                L.h[3 * (size_t)p + 0] = Vi[0] * g[0] + Vi[1] * g[1] + Vi[2] * g[2];
+                L.h[3 * (size_t)p + 1] = Vi[1] * g[0] + Vi[3] * g[1] + Vi[4] * g[2];
+                L.h[3 * (size_t)p + 2] = Vi[2] * g[0] + Vi[4] * g[1] + Vi[5] * g[2];
+                const double *s = L.sp + 3 * (size_t)p;
+                gmax = fmax(gmax, fmax(fabs(g[0] / s[0]), fmax(fabs(g[1] / s[1]), fabs(g[2] / s[2]))));
+            }
+        } else if (lane == 0) {
+            L.h[3 * (size_t)p] = L.h[3 * (size_t)p + 1] = L.h[3 * (size_t)p + 2] = 0.0;
+        }
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int i = ch * kChunk + lane;
+            if (nchunks > 1) {
+                lo.active = false;
+                if (i < kn) lin_obs(P, x, k, L, k0 + i, p, pvar, lo);
+            }
+            if (i < kn) {
+                double2 *rec = reinterpret_cast<double2 *>(L.Tt + 18 * (size_t)(k0 + i));
+                if (lo.active && pvar) {
+                    double T[18];
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+                        const double w0 = lo.Jc[a] * lo.JX[0] + lo.Jc[6 + a] * lo.JX[3];
+                        const double w1 = lo.Jc[a] * lo.JX[1] + lo.Jc[6 + a] * lo.JX[4];
+                        const double w2 = lo.Jc[a] * lo.JX[2] + lo.Jc[6 + a] * lo.JX[5];
+                        const double t0 = w0 / l00;                          // t Lc^T = w
+                        const double t1 = (w1 - l10 * t0) / l11;
+                        const double t2 = (w2 - l20 * t0 - l21 * t1) / l22;
+                        T[a * 3] = t0, T[a * 3 + 1] = t1, T[a * 3 + 2] = t2;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) rec[j] = make_double2(T[2 * j], T[2 * j + 1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) rec[j] = make_double2(0.0, 0.0);
+                }
+            }
+        }
+    }
+    if (lane == 0 && gmax > 0.0) atomic_max_nonneg(&scalars[SC_GRAD_MAX_PT], gmax);
+}
+
+int ba_launch_lin(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k, const BALinSys &L,
+                  double inv_radius, double *scalars, cudaStream_t st) {
+    if (P.n_pts_local > 0) {
+        k_lin<<<point_grid(P.n_pts_local), kWarpsPerCta * 32, 0, st>>>(P, x, k, L, inv_radius, scalars);
+        XRB_LAUNCHED();
+    }
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+__device__ __forceinline__ void load_rec(const double *__restrict__ Tt, int o, double T[18]) {
+    const double2 *r = reinterpret_cast<const double2 *>(Tt + 18 * (size_t)o);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const double2 v = __ldg(r + j);
+        T[2 * j] = v.x, T[2 * j + 1] = v.y;
+    }
+}
+
+constexpr int kLanesPerBlock = 8;
+
+__global__ void __launch_bounds__(256)
+k_gather(BAProblemDev P, BALinSys L) {
+    const int sub = threadIdx.x & (kLanesPerBlock - 1);
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) / kLanesPerBlock;
+    const bool live = b < P.n_blocks;
+    double acc[36];
+#pragma unroll
+    for (int j = 0; j < 36; ++j) acc[j] = 0.0;
+    if (live) {
+        const int i0 = P.blk_ptr[b], i1 = P.blk_ptr[b + 1];
+        for (int it = i0 + sub; it < i1; it += kLanesPerBlock) {
+            const int2 oo = __ldg(P.inc + it);
+            double Ti[18], Tj[18];
+            load_rec(L.Tt, oo.x, Ti);
+            load_rec(L.Tt, oo.y, Tj);
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+                    acc[a * 6 + c] += Ti[a * 3] * Tj[c * 3] + Ti[a * 3 + 1] * Tj[c * 3 + 1] + Ti[a * 3 + 2] * Tj[c * 3 + 2];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 36; ++j) {
+        double v = acc[j];
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+        acc[j] = v;
+    }
+    if (!live) return;
+    const int2 cams = P.blk_cams[b];
+    int ra[6], cb[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        ra[j] = P.colq[cams.x] >= 0 ? P.colq[cams.x] + j : -1, ra[3 + j] = P.colt[cams.x] >= 0 ? P.colt[cams.x] + j : -1;
+        cb[j] = P.colq[cams.y] >= 0 ? P.colq[cams.y] + j : -1, cb[3 + j] = P.colt[cams.y] >= 0 ? P.colt[cams.y] + j : -1;
+    }
+    const bool same = cams.x == cams.y;  // two observations of one camera on one point: M + M^T
+    // the 8 lanes of the group share the 36 stores
+#pragma unroll
+    for (int e = 0; e < 36; ++e) {
+        if ((e & (kLanesPerBlock - 1)) != sub) continue;
+        const int a = e / 6, c = e % 6;
+        if (ra[a] < 0 || cb[c] < 0) continue;
+        if (same) {
+            if (c > a) continue;
+            L.S[(size_t)ra[a] * L.ld + cb[c]] = -(acc[a * 6 + c] + acc[c * 6 + a]);
+        } else {
+            L.S[(size_t)ra[a] * L.ld + cb[c]] = -acc[e];
+        }
+    }
+}
+
+int ba_launch_gather(const BAProblemDev &P, const BALinSys &L, cudaStream_t st) {
+    if (P.n_blocks > 0) {
+        const long long threads = (long long)P.n_blocks * kLanesPerBlock;
+        k_gather<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, L);
+        XRB_LAUNCHED();
+    }
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+__global__ void __launch_bounds__(128)
+k_cam_blocks(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L) {
+    const int c = blockIdx.x;
+    const int cq = P.colq[c], ct = P.colt[c];
+    if (cq < 0 && ct < 0) return;
+    // 21 lower entries of (Jc^T Jc), 21 of (Tt Tt^T), 6 g_c, 6 rhs
+    double acc[54];
+#pragma unroll
+    for (int j = 0; j < 54; ++j) acc[j] = 0.0;
+    const int o0 = P.cam_ptr[c], o1 = P.cam_ptr[c + 1];
+    for (int it = o0 + threadIdx.x; it < o1; it += 128) {
+        const int o = P.cam_obs[it];
+        const int p = P.obs_pt[o];
+        const bool pvar = P.pt_var[p] != 0;
+        LinObs lo;
+        lin_obs(P, x, k, L, o, p, pvar, lo);
+        if (!lo.active) continue;
+        double T[18];
+        load_rec(L.Tt, o, T);
+        const double h0 = L.h[3 * (size_t)p], h1 = L.h[3 * (size_t)p + 1], h2 = L.h[3 * (size_t)p + 2];
+        // r - JX h
+        const double e0 = lo.r0 - (lo.JX[0] * h0 + lo.JX[1] * h1 + lo.JX[2] * h2);
+        const double e1 = lo.r1 - (lo.JX[3] * h0 + lo.JX[4] * h1 + lo.JX[5] * h2);
+        int w = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+#pragma unroll
+            for (int b = 0; b <= a; ++b, ++w) {
+                acc[w] += lo.Jc[a] * lo.Jc[b] + lo.Jc[6 + a] * lo.Jc[6 + b];
+                acc[21 + w] += T[a * 3] * T[b * 3] + T[a * 3 + 1] * T[b * 3 + 1] + T[a * 3 + 2] * T[b * 3 + 2];
+            }
+            acc[42 + a] += lo.Jc[a] * lo.r0 + lo.Jc[6 + a] * lo.r1;
+            acc[48 + a] += lo.Jc[a] * e0 + lo.Jc[6 + a] * e1;
+        }
+    }
+    __shared__ double red[4][54];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 54; ++j) {
+        const double v = warp_sum(acc[j]);
+        if (lane == 0) red[wrp][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 54) {
+        const int j = threadIdx.x;
+        const double v = red[0][j] + red[1][j] + red[2][j] + red[3][j];
+        int cols[6];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) cols[q] = cq >= 0 ? cq + q : -1, cols[3 + q] = ct >= 0 ? ct + q : -1;
+        if (j < 42) {
+            int w = j < 21 ? j : j - 21, a = 0;
+            while (w >= a + 1) w -= a + 1, ++a;  // w-th lower entry -> (a, b = w)
+            const int b = w;
+            if (cols[a] >= 0 && cols[b] >= 0) {
+                if (j < 21)
+                    L.U[(size_t)cols[a] * 6 + b] = v;
+                else
+                    L.S[(size_t)cols[a] * L.ld + cols[b]] -= v;  // += -Tt Tt^T on top of k_gather's part
+            }
+        } else if (j < 48) {
+            if (cols[j - 42] >= 0) L.gc[cols[j - 42]] = v;
+        } else {
+            if (cols[j - 48] >= 0) L.S[(size_t)P.nc * L.ld + cols[j - 48]] = v;  // rhs row
+        }
+    }
+}
+
+int ba_launch_cam_blocks(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k, const BALinSys &L,
+                         cudaStream_t st) {
+    if (P.n_cams > 0) {
+        k_cam_blocks<<<P.n_cams, 128, 0, st>>>(P, x, k, L);
+        XRB_LAUNCHED();
+    }
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+// =====================================================================================
 // 3a. Camera block-diagonal: S += U + D_c^2 with D_c^2 = clamp(diag U, 1e-6, 1e32)/radius,
 //     and the camera part of the gradient max-norm ||x - Plus(x, -g)||_inf.
 //     Runs after the exchange (U, gc are global sums).

@@ -14,6 +14,7 @@
 // (cost_factor_ceres.h:19-40) and the camera models (camera_model.hpp:93-210).
 #pragma once
 #include <cstdint>
+#include <vector>
 
 #include "common.cuh"
 
@@ -35,6 +36,13 @@ struct BAProblemDev {
     const int32_t *obs_cam;                     // [n_obs_local] (point-major order)
     const double *obs_uv;                       // [2 * n_obs_local]
     const uint8_t *pt_var;                      // [n_pts_local]
+    // generation-2 Schur structure (ba_struct.cu); n_blocks < 0 selects generation 1
+    const int32_t *obs_pt;                      // [n_obs_local] local point of each observation
+    const int32_t *cam_ptr, *cam_obs;           // camera-major CSR of point-major obs indices
+    int n_blocks;                               // off-diagonal 6x6 blocks of S with >= 1 point
+    const int32_t *blk_ptr;                     // [n_blocks + 1] offsets into inc
+    const int2 *blk_cams;                       // [n_blocks] (cam_a, cam_b), cols(a) >= cols(b)
+    const int2 *inc;                            // (obs_i of cam_a, obs_j of cam_b), same point
 };
 
 // Mutable state: a set of (q, t, X) arrays.
@@ -53,6 +61,8 @@ struct BALinSys {
     double *U, *gc, *n2c;
     double *Vinv, *gp;  // per local point: V^-1 (6), g_p (3)
     double *sc, *sp;    // Jacobi scaling: camera columns [nc], point columns [3 * n_pts_local]
+    double *Tt;         // generation 2: per observation W (V + D^2)^-1/2  (6 x 3 = 18 doubles)
+    double *h;          // generation 2: per local point (V + D^2)^-1 g_p  (3 doubles)
 };
 
 // scalar slots (doubles) produced on the device, read by the host controller
@@ -73,6 +83,16 @@ int ba_launch_colnorm(const BAProblemDev &P, const BAStateDev &x, const BAConsts
 int ba_launch_finish_scaling(const BAProblemDev &P, const BALinSys &L, cudaStream_t st);
 int ba_launch_schur(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
                     const BALinSys &L, double inv_radius, double *scalars, cudaStream_t st);
+// generation 2: linearise (per-observation records, no atomics) -> gather per block ->
+// camera-major diagonal blocks / gradient / rhs
+int ba_launch_lin(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
+                  const BALinSys &L, double inv_radius, double *scalars, cudaStream_t st);
+int ba_launch_gather(const BAProblemDev &P, const BALinSys &L, cudaStream_t st);
+int ba_launch_cam_blocks(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
+                         const BALinSys &L, cudaStream_t st);
+int ba_build_block_lists(const BAProblemDev &P, const std::vector<int64_t> &pair_ptr_host, DevBuf &d_inc,
+                         DevBuf &d_blk_ptr, DevBuf &d_blk_cams, int *n_blocks, int64_t *n_inc,
+                         cudaStream_t st);
 int ba_launch_cam_diag(const BAProblemDev &P, const BAStateDev &x, const BALinSys &L,
                        double inv_radius, double *scalars, cudaStream_t st);
 int ba_launch_backsub(const BAProblemDev &P, const BAStateDev &x, const BAStateDev &cand,

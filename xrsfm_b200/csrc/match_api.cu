@@ -30,6 +30,7 @@ struct xrb_matcher {
     int chunk_pairs = 0, state_stride = 0;
     DevBuf rows_best, rows_second, cols_best, cols_second;
     DevBuf pairdesc, counts, strided, packed, pack_offsets, vlow, pair_idx;
+    DevBuf dist_tab;  // float(acos(double(min(v*2^-18,1)))) for v = 0..2^18 (generation 3)
     int strided_stride = 0;
 };
 
@@ -66,7 +67,7 @@ int score(xrb_matcher *m, const PairDesc *pd_dev, int n, int max_n1, int max_n2,
           cudaStream_t st, bool slots = false) {
     Top2State rows{m->rows_best.as<unsigned long long>(), m->rows_second.as<unsigned int>()};
     Top2State cols{m->cols_best.as<unsigned long long>(), m->cols_second.as<unsigned int>()};
-    if (m->variant == 2) {
+    if (m->variant >= 2) {
         if (slots)
             return launch_score_tc(pd_dev, n, m->slot[0].as<uint8_t>(), (uint64_t)m->max_features,
                                    m->slot[1].as<uint8_t>(), (uint64_t)m->max_features,
@@ -77,6 +78,24 @@ int score(xrb_matcher *m, const PairDesc *pd_dev, int n, int max_n1, int max_n2,
     }
     return launch_score_dp4a(pd_dev, n, max_n1, max_n2, m->state_stride, rows, cols,
                              m->vlow.as<int>(), st);
+}
+
+// generation 3 applies when every image of the call fits the fused kernel's shared-memory state
+bool use_fused(const xrb_matcher *m, int max_feat) {
+    return m->variant == 3 && max_feat <= fused_max_features() && m->dist_tab.p != nullptr;
+}
+
+int match_fused(xrb_matcher *m, const PairDesc *pd_dev, int n, bool slots, float distmax, float ratiomax, int mbm,
+                int max_match, int32_t *counts_dev, uint32_t (*out_dev)[2], int out_stride, cudaStream_t st) {
+    const uint8_t *bA, *bB;
+    uint64_t rA, rB;
+    if (slots) {
+        bA = m->slot[0].as<uint8_t>(), bB = m->slot[1].as<uint8_t>(), rA = rB = (uint64_t)m->max_features;
+    } else {
+        bA = bB = m->block, rA = rB = (uint64_t)m->offsets[m->n_images];
+    }
+    return launch_match_fused(pd_dev, n, bA, rA, bB, rB, m->vlow.as<int>(), m->dist_tab.as<float>(), distmax,
+                              ratiomax, mbm, max_match, counts_dev, out_dev, out_stride, st);
 }
 
 int finalize(xrb_matcher *m, const PairDesc *pd_dev, int n, float distmax, float ratiomax,
@@ -103,7 +122,14 @@ xrb_matcher *xrb_match_create(int max_features, int device) {
         delete m;
         return nullptr;
     }
-    m->variant = score_tc_available() ? 2 : 1;
+    m->variant = score_tc_available() ? 3 : 1;
+    if (m->dist_tab.reserve(262145 * sizeof(float)) != XRB_OK ||
+        launch_dist_table(m->dist_tab.as<float>(), 262145, m->stream) != XRB_OK ||
+        cudaStreamSynchronize(m->stream) != cudaSuccess) {
+        set_error("matcher: building the distance table failed");
+        xrb_match_destroy(m);
+        return nullptr;
+    }
     return m;
 }
 
@@ -114,7 +140,7 @@ void xrb_match_destroy(xrb_matcher *m) {
     DevBuf *bufs[] = {&m->images, &m->offsets_dev, &m->slot[0], &m->slot[1], &m->rows_best,
                       &m->rows_second, &m->cols_best, &m->cols_second, &m->pairdesc,
                       &m->counts, &m->strided, &m->packed, &m->pack_offsets, &m->vlow,
-                      &m->pair_idx};
+                      &m->pair_idx, &m->dist_tab};
     for (DevBuf *b : bufs) b->release();
     cudaStreamDestroy(m->stream);
     delete m;
@@ -124,9 +150,9 @@ int xrb_match_max_features(const xrb_matcher *m) { return m ? m->max_features : 
 
 int xrb_match_set_variant(xrb_matcher *m, int variant) {
     if (!m) return XRB_ERR_INVALID;
-    if (variant == 0) variant = score_tc_available() ? 2 : 1;
-    if (variant == 2 && !score_tc_available()) variant = 1;
-    if (variant != 1 && variant != 2) {
+    if (variant == 0) variant = score_tc_available() ? 3 : 1;
+    if (variant >= 2 && !score_tc_available()) variant = 1;
+    if (variant < 1 || variant > 3) {
         set_error("unknown matcher variant %d", variant);
         return XRB_ERR_INVALID;
     }
@@ -172,10 +198,16 @@ int xrb_match_get(xrb_matcher *m, int max_match, uint32_t (*match_buffer)[2], fl
         cudaSuccess)
         return -1;
     if (launch_vlow(distmax, ratiomax, m->vlow.as<int>(), st)) return -1;
-    if (score(m, m->pairdesc.as<PairDesc>(), 1, n1, n2, st, true)) return -1;
-    if (finalize(m, m->pairdesc.as<PairDesc>(), 1, distmax, ratiomax, mutual_best_match,
-                 max_match, m->counts.as<int32_t>(), m->strided.as<uint32_t[2]>(), stride, st))
-        return -1;
+    if (use_fused(m, std::max(n1, n2))) {
+        if (match_fused(m, m->pairdesc.as<PairDesc>(), 1, true, distmax, ratiomax, mutual_best_match, max_match,
+                        m->counts.as<int32_t>(), m->strided.as<uint32_t[2]>(), stride, st))
+            return -1;
+    } else {
+        if (score(m, m->pairdesc.as<PairDesc>(), 1, n1, n2, st, true)) return -1;
+        if (finalize(m, m->pairdesc.as<PairDesc>(), 1, distmax, ratiomax, mutual_best_match,
+                     max_match, m->counts.as<int32_t>(), m->strided.as<uint32_t[2]>(), stride, st))
+            return -1;
+    }
     int32_t n = 0;
     if (cudaMemcpyAsync(&n, m->counts.p, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
         return -1;
@@ -292,6 +324,12 @@ int xrb_match_pairs_device(xrb_matcher *m, int n_pairs, const int32_t (*pairs_de
         if ((rc = launch_build_pairs(pairs_dev + p0, n, m->offsets_dev.as<int64_t>(), m->block,
                                      m->max_features, pd, st)))
             return rc;
+        if (use_fused(m, max_feat)) {
+            if ((rc = match_fused(m, pd, n, false, distmax, ratiomax, mutual_best_match, max_match, counts_dev + p0,
+                                  out_dev + (size_t)p0 * out_stride, out_stride, st)))
+                return rc;
+            continue;
+        }
         if ((rc = score(m, pd, n, max_feat, max_feat, st))) return rc;
         if ((rc = finalize(m, pd, n, distmax, ratiomax, mutual_best_match, max_match,
                            counts_dev + p0, out_dev + (size_t)p0 * out_stride, out_stride, st)))
@@ -342,10 +380,16 @@ int xrb_match_pairs(xrb_matcher *m, int n_pairs, const int32_t (*pairs)[2], floa
                                      m->offsets_dev.as<int64_t>(), m->block, m->max_features,
                                      pd, st)))
             return rc;
-        if ((rc = score(m, pd, n, max_feat, max_feat, st))) return rc;
-        if ((rc = finalize(m, pd, n, distmax, ratiomax, mutual_best_match, max_match,
-                           m->counts.as<int32_t>(), m->strided.as<uint32_t[2]>(), stride, st)))
-            return rc;
+        if (use_fused(m, max_feat)) {
+            if ((rc = match_fused(m, pd, n, false, distmax, ratiomax, mutual_best_match, max_match,
+                                  m->counts.as<int32_t>(), m->strided.as<uint32_t[2]>(), stride, st)))
+                return rc;
+        } else {
+            if ((rc = score(m, pd, n, max_feat, max_feat, st))) return rc;
+            if ((rc = finalize(m, pd, n, distmax, ratiomax, mutual_best_match, max_match,
+                               m->counts.as<int32_t>(), m->strided.as<uint32_t[2]>(), stride, st)))
+                return rc;
+        }
         if ((rc = launch_pack(m->counts.as<int32_t>(), n, m->strided.as<uint32_t[2]>(), stride,
                               m->pack_offsets.as<int64_t>(), m->packed.as<uint32_t[2]>(), 0,
                               (int64_t)chunk * stride, st)))

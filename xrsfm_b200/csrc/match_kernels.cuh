@@ -62,6 +62,15 @@ int launch_score_tc(const PairDesc *pairs_dev, int n_pairs, const uint8_t *baseA
                     Top2State cols, const int *vlow_dev, cudaStream_t st);
 bool score_tc_available();
 
+// Generation 3: the same tensor-core kernel with the pair's top-2 state in shared memory and
+// thresholds + mutual test + ordered compaction fused in (images up to fused_max_features()
+// descriptors).  dist_tab = launch_dist_table output for v = 0 .. 2^18.
+int fused_max_features();
+int launch_match_fused(const PairDesc *pairs_dev, int n_pairs, const uint8_t *baseA, uint64_t rowsA,
+                       const uint8_t *baseB, uint64_t rowsB, const int *vlow_dev, const float *dist_tab,
+                       float distmax, float ratiomax, int mbm, int max_match, int32_t *counts_dev,
+                       uint32_t (*out_dev)[2], int out_stride, cudaStream_t st);
+
 int launch_finalize(const PairDesc *pairs_dev, int n_pairs, int state_stride, Top2State rows,
                     Top2State cols, float distmax, float ratiomax, int mbm, int max_match,
                     int32_t *counts_dev, uint32_t (*out_dev)[2], int out_stride,

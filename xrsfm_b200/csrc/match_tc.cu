@@ -27,13 +27,25 @@ namespace {
 
 constexpr int kTileM = 128;          // descriptors of image 1 per MMA tile (TMEM lanes)
 constexpr int kTileN = 256;          // descriptors of image 2 per MMA tile (TMEM columns)
-constexpr int kGroupN = 1024;        // resident B descriptors per group
 constexpr int kAStages = 3;
 constexpr int kATileBytes = kTileM * kDim;    // 16 KB
-constexpr int kBGroupBytes = kGroupN * kDim;  // 128 KB
 constexpr int kBoxRows = 128;                 // TMA box: 128 rows x 128 bytes
 constexpr int kThreads = 32 * 10;
-constexpr int kSmemBytes = kBGroupBytes + kAStages * kATileBytes + 1024 /*align*/ + 256 /*barriers*/;
+// Two flavours of the kernel (template parameter kFused):
+//  false: top-2 state in global memory (any image size), resident B group of 1024 descriptors,
+//         thresholds/compaction in finalize_kernel afterwards;
+//  true : images up to kFusedMax descriptors: the pair's whole top-2 state lives in shared
+//         memory as one packed 64-bit word per row/column, candidates go through per-warp
+//         queues, and thresholds + mutual test + ordered compaction run in the same kernel.
+constexpr int kFusedMax = 4096;
+template <bool kFused> struct Cfg {
+    static constexpr int kGroupN = kFused ? 768 : 1024;  // resident B descriptors per group
+    static constexpr int kBGroupBytes = kGroupN * kDim;
+    static constexpr int kStateBytes = kFused ? 2 * kFusedMax * 8 : 0;
+    static constexpr int kQueueBytes = kFused ? 8 * 64 * 8 : 0;
+    static constexpr int kSmemBytes = kBGroupBytes + kAStages * kATileBytes + kStateBytes + kQueueBytes +
+                                      1024 /*align*/ + 256 /*barriers*/;
+};
 
 // ---- PTX helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -113,17 +125,68 @@ struct Bars {
     uint32_t tmem_base;
 };
 
+// ---- fused mode: packed top-2 word ----------------------------------------------------------
+//   [63:41] best dot (23 bits)   [40:28] 8191 - tie_rank (13 bits)   [27:5] runner-up dot (23 bits)
+// 0 == empty.  One 64-bit shared-memory CAS loop per update keeps best, argmax and runner-up
+// consistent; the update rule is the reference's (ProgramCU.cu:1802-1807): a strictly larger
+// (dot, tie order) takes over and demotes the old best to runner-up, anything else only feeds
+// the runner-up.
+__device__ __forceinline__ uint32_t rank13_row(uint32_t j) { return (bitrev5(j & 31u) << 8) | (j >> 5); }
+__device__ __forceinline__ uint32_t unrank13_row(uint32_t r) { return ((r & 0xFFu) << 5) | bitrev5(r >> 8); }
+
+__device__ __forceinline__ void top2_update(unsigned long long *addr, uint32_t v, uint32_t rk) {
+    unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(addr), assumed;
+    const unsigned long long keyc = ((unsigned long long)v << 13) | rk;
+    do {
+        assumed = old;
+        unsigned long long nw;
+        if (keyc > (assumed >> 28)) {
+            nw = (keyc << 28) | ((assumed >> 41) << 5);
+        } else {
+            const uint32_t sec = (uint32_t)(assumed >> 5) & 0x7FFFFFu;
+            if (sec >= v) return;
+            nw = (assumed & ~(0x7FFFFFull << 5)) | ((unsigned long long)v << 5);
+        }
+        old = atomicCAS(addr, assumed, nw);
+    } while (old != assumed);
+}
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+struct FusedArgs {
+    const float *dist_tab;  // float(acos(double(min(v * 2^-18, 1)))) for v = 0 .. 2^18
+    float distmax, ratiomax;
+    int mbm, max_match;
+    int32_t *counts;
+    uint32_t (*out)[2];
+    int out_stride;
+};
+
+__device__ __forceinline__ bool accept_tab(const float *__restrict__ tab, uint32_t best, uint32_t second,
+                                           float distmax, float ratiomax) {
+    const float dist = __ldg(tab + min(best, 262144u));
+    const float distn = __ldg(tab + min(second, 262144u));
+    return (dist < distmax) && (dist < distn * ratiomax);
+}
+
+template <bool kFused>
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const uint8_t *baseA, const uint8_t *baseB, const PairDesc *__restrict__ pairs,
                 int n_pairs, int state_stride, Top2State rows, Top2State cols,
-                const int *__restrict__ vlow_ptr) {
+                const int *__restrict__ vlow_ptr, FusedArgs fa) {
+    using C = Cfg<kFused>;
+    constexpr int kGroupN = C::kGroupN;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024 B alignment
     const uint32_t sB = base;
-    const uint32_t sA = base + kBGroupBytes;
-    Bars *bars = reinterpret_cast<Bars *>(smem_raw + (base - raw) + kBGroupBytes + kAStages * kATileBytes);
+    const uint32_t sA = base + C::kBGroupBytes;
+    unsigned char *after = smem_raw + (base - raw) + C::kBGroupBytes + kAStages * kATileBytes;
+    unsigned long long *st_rows = reinterpret_cast<unsigned long long *>(after);  // [kFusedMax]
+    unsigned long long *st_cols = st_rows + (kFused ? kFusedMax : 0);             // [kFusedMax]
+    unsigned long long *queues = st_cols + (kFused ? kFusedMax : 0);              // [8][64]
+    Bars *bars = reinterpret_cast<Bars *>(after + C::kStateBytes + C::kQueueBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -212,13 +275,37 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     } else {
         // ===================== epilogue =====================
         const int ew = warp - 2;            // 0..7
+        const int et = threadIdx.x - 64;    // 0..255 among the epilogue threads
         const int quarter = warp & 3;       // TMEM lane quarter this warp may touch (warp id % 4)
         const int half = ew >> 2;           // which 128-column half of the 256-column tile
         const int vlow = *vlow_ptr;
+        unsigned long long *q = queues + ew * 64;
+        int qn = 0;                          // warp-uniform queue fill
+        const unsigned lt_mask = (1u << lane) - 1u;
         uint32_t t_it = 0;
+        if (kFused) {
+            for (int z = et; z < 2 * kFusedMax; z += 256) st_rows[z] = 0ull;
+            epi_bar();
+        }
+        auto drain = [&]() {
+            __syncwarp();
+            for (int b0 = 0; b0 < qn; b0 += 32) {
+                if (b0 + lane < qn) {
+                    const unsigned long long e = q[b0 + lane];
+                    const uint32_t v = (uint32_t)(e >> 26), i = (uint32_t)(e >> 13) & 0x1FFFu, j = (uint32_t)e & 0x1FFFu;
+                    top2_update(st_rows + i, v, 8191u - rank13_row(j));
+                    top2_update(st_cols + j, v, 8191u - i);
+                }
+            }
+            __syncwarp();
+            qn = 0;
+        };
         for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
             const PairDesc pd = pairs[p];
-            if (pd.n1 <= 0 || pd.n2 <= 0) continue;
+            if (pd.n1 <= 0 || pd.n2 <= 0) {
+                if (kFused && et == 0) fa.counts[p] = 0;
+                continue;
+            }
             const size_t sbase = (size_t)p * state_stride;
             const int mt = (pd.n1 + kTileM - 1) / kTileM;
             for (int g0 = 0; g0 < pd.n2; g0 += kGroupN) {
@@ -257,7 +344,26 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                 int mx = v[g];
 #pragma unroll
                                 for (int e = 1; e < 16; ++e) mx = max(mx, v[g + e]);
-                                if (mx > vlow && i < pd.n1) {
+                                if (kFused) {
+                                    // warp-uniform slow path: candidates are appended to the warp's
+                                    // queue with ballot-derived slots (no atomics), drained 32 at a time
+                                    if (__any_sync(0xFFFFFFFFu, mx > vlow && i < pd.n1)) {
+#pragma unroll
+                                        for (int e = 0; e < 16; ++e) {
+                                            const int val = v[g + e], j = j0 + g + e;
+                                            const bool c = val > vlow && i < pd.n1 && j < pd.n2;
+                                            const unsigned mk = __ballot_sync(0xFFFFFFFFu, c);
+                                            if (mk) {
+                                                if (c)
+                                                    q[qn + __popc(mk & lt_mask)] =
+                                                        ((unsigned long long)(unsigned)val << 26) |
+                                                        ((unsigned long long)(unsigned)i << 13) | (unsigned)j;
+                                                qn += __popc(mk);
+                                                if (qn > 32) drain();
+                                            }
+                                        }
+                                    }
+                                } else if (mx > vlow && i < pd.n1) {
 #pragma unroll
                                     for (int e = 0; e < 16; ++e) {
                                         const int val = v[g + e], j = j0 + g + e;
@@ -275,6 +381,52 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         }
                     }
                 }
+            }
+            if (kFused) {
+                // ---- the pair is complete: thresholds, mutual test, ordered compaction -------
+                // (RowMatch/ColMatch threshold lines + SiftMatchCU.cpp:199-207), then wipe the state
+                drain();
+                epi_bar();
+                int *wsum = reinterpret_cast<int *>(queues);  // queues are idle now
+                int running = 0;
+                uint32_t(*dst)[2] = fa.out + (size_t)p * fa.out_stride;
+                for (int chunk = 0; chunk < pd.n1; chunk += 256) {
+                    const int r = chunk + et;
+                    int flag = 0, j = -1;
+                    if (r < pd.n1) {
+                        const unsigned long long sr = st_rows[r];
+                        const uint32_t bv = (uint32_t)(sr >> 41);
+                        if (bv > 0 && accept_tab(fa.dist_tab, bv, (uint32_t)(sr >> 5) & 0x7FFFFFu, fa.distmax, fa.ratiomax)) {
+                            j = (int)unrank13_row(8191u - ((uint32_t)(sr >> 28) & 0x1FFFu));
+                            if (fa.mbm) {
+                                const unsigned long long sc = st_cols[j];
+                                const uint32_t cv = (uint32_t)(sc >> 41);
+                                flag = cv > 0 && (int)(8191u - ((uint32_t)(sc >> 28) & 0x1FFFu)) == r &&
+                                       accept_tab(fa.dist_tab, cv, (uint32_t)(sc >> 5) & 0x7FFFFFu, fa.distmax, fa.ratiomax);
+                            } else {
+                                flag = 1;
+                            }
+                        }
+                    }
+                    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, flag);
+                    if (lane == 0) wsum[ew] = __popc(ballot);
+                    epi_bar();
+                    int before = 0, total = 0;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        const int c = wsum[w];
+                        before += w < ew ? c : 0;
+                        total += c;
+                    }
+                    const int pos = running + before + __popc(ballot & lt_mask);
+                    if (flag && pos < fa.max_match) dst[pos][0] = (uint32_t)r, dst[pos][1] = (uint32_t)j;
+                    running += total;
+                    epi_bar();
+                }
+                if (et == 0) fa.counts[p] = running < fa.max_match ? running : fa.max_match;
+                for (int z = et; z < pd.n1; z += 256) st_rows[z] = 0ull;
+                for (int z = et; z < pd.n2; z += 256) st_cols[z] = 0ull;
+                epi_bar();
             }
         }
     }
@@ -336,9 +488,11 @@ bool score_tc_available() {
     return get_encode() != nullptr;
 }
 
-int launch_score_tc(const PairDesc *pairs_dev, int n_pairs, const uint8_t *baseA, uint64_t rowsA,
-                    const uint8_t *baseB, uint64_t rowsB, int state_stride, Top2State rows, Top2State cols,
-                    const int *vlow_dev, cudaStream_t st) {
+namespace {
+template <bool kFused>
+int launch_impl(const PairDesc *pairs_dev, int n_pairs, const uint8_t *baseA, uint64_t rowsA, const uint8_t *baseB,
+                uint64_t rowsB, int state_stride, Top2State rows, Top2State cols, const int *vlow_dev,
+                const FusedArgs &fa, cudaStream_t st) {
     if (n_pairs <= 0) return XRB_OK;
     if (((uintptr_t)baseA & 15) || ((uintptr_t)baseB & 15)) {
         set_error("tcgen05 matcher: descriptor blocks must be 16-byte aligned");
@@ -350,18 +504,39 @@ int launch_score_tc(const PairDesc *pairs_dev, int n_pairs, const uint8_t *baseA
     if ((rc = make_map(&mapB, baseB, rowsB))) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        XRB_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        XRB_CUDA(cudaFuncSetAttribute(score_tc_kernel<kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg<kFused>::kSmemBytes));
         attr_set = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = n_pairs < sms ? n_pairs : sms;
-    score_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(mapA, mapB, baseA, baseB, pairs_dev, n_pairs, state_stride,
-                                                        rows, cols, vlow_dev);
+    score_tc_kernel<kFused><<<grid, kThreads, Cfg<kFused>::kSmemBytes, st>>>(
+        mapA, mapB, baseA, baseB, pairs_dev, n_pairs, state_stride, rows, cols, vlow_dev, fa);
     XRB_LAUNCHED();
     XRB_CUDA(cudaGetLastError());
     return XRB_OK;
+}
+}  // namespace
+
+int launch_score_tc(const PairDesc *pairs_dev, int n_pairs, const uint8_t *baseA, uint64_t rowsA,
+                    const uint8_t *baseB, uint64_t rowsB, int state_stride, Top2State rows, Top2State cols,
+                    const int *vlow_dev, cudaStream_t st) {
+    FusedArgs fa{};
+    return launch_impl<false>(pairs_dev, n_pairs, baseA, rowsA, baseB, rowsB, state_stride, rows, cols, vlow_dev,
+                              fa, st);
+}
+
+int fused_max_features() { return kFusedMax; }
+
+int launch_match_fused(const PairDesc *pairs_dev, int n_pairs, const uint8_t *baseA, uint64_t rowsA,
+                       const uint8_t *baseB, uint64_t rowsB, const int *vlow_dev, const float *dist_tab,
+                       float distmax, float ratiomax, int mbm, int max_match, int32_t *counts_dev,
+                       uint32_t (*out_dev)[2], int out_stride, cudaStream_t st) {
+    FusedArgs fa{dist_tab, distmax, ratiomax, mbm, max_match, counts_dev, out_dev, out_stride};
+    Top2State none{nullptr, nullptr};
+    return launch_impl<true>(pairs_dev, n_pairs, baseA, rowsA, baseB, rowsB, 0, none, none, vlow_dev, fa, st);
 }
 
 }  // namespace xrb
