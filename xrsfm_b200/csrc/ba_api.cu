@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -117,8 +118,21 @@ int upload(DevBuf &b, const T *src, size_t n, cudaStream_t st) {
     return XRB_OK;
 }
 
+struct LoadTimer {  // XRB_BA_DEBUG=1 prints where xrb_ba_load spends its time
+    bool on = getenv("XRB_BA_DEBUG") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[xrb_ba_load] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
 int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
     XRB_CUDA(cudaSetDevice(s->device));
+    LoadTimer lt;
     cudaStream_t st = s->own_stream;
     if (!P || P->n_cams < 0 || P->n_pts < 0 || P->n_obs < 0 || P->n_intr <= 0 || !P->cam_q || !P->cam_t ||
         !P->pts || !P->intr || !P->intr_model || !P->cam_intr || (P->n_obs && (!P->obs_cam || !P->obs_pt || !P->obs_uv))) {
@@ -142,6 +156,7 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
             return XRB_ERR_INVALID;
         }
     s->C = C, s->P_total = NP, s->O_total = NO, s->n_intr = P->n_intr;
+    lt.lap("validate");
 
     // ---- global structure: CSR by point (stable), variable blocks, reduced columns
     std::vector<int> pt_ptr(NP + 1, 0), cam_obs(C, 0);
@@ -181,6 +196,7 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
         if (hi >= 0) bw = std::max(bw, hi - lo);
     }
     s->bw = std::max(bw, 5);
+    lt.lap("csr + columns + bandwidth");
 
     // ---- shard the points over ranks, balanced by the Schur work (xrb_ba_shard_range)
     int p_lo = 0, p_hi = NP;
@@ -221,6 +237,7 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
         if ((rc = upload(s->d_X[i], P->pts + 3 * (size_t)p_lo, 3 * (size_t)s->P_local, st))) return rc;
     }
     s->cur = 0;
+    lt.lap("shard + uploads");
     // ---- generation-2 Schur structure: obs -> point, camera-major CSR, block incidence lists
     {
         const char *env = getenv("XRB_BA_SCHUR");
@@ -248,8 +265,10 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
             if ((rc = s->d_h.reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
             BAProblemDev pd = s->prob();
             pd.nc = s->nc;
+            lt.lap("cam-major csr + uploads");
             if ((rc = ba_build_block_lists(pd, pair_ptr, s->d_inc, s->d_blk_ptr, s->d_blk_cams, &s->n_blocks, &s->n_inc, st)))
                 return rc;
+            lt.lap("block lists (device)");
         }
     }
     // ---- linear-system storage
@@ -274,6 +293,7 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
         return XRB_ERR_INVALID;
     }
     XRB_CUDA(cudaStreamSynchronize(st));
+    lt.lap("linear-system buffers");
     s->loaded = true;
     return XRB_OK;
 }

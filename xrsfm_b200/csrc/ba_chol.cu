@@ -21,61 +21,55 @@
 namespace xrb {
 
 constexpr int NB = 64;  // block-column width == GEMM depth
-constexpr int kDiagSmem = (2 * NB * (NB + 1) + NB) * (int)sizeof(double);
 
 // ---- 1. diagonal block ---------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// 64 threads, thread r keeps row r of the block in registers (fully unrolled, static
+// indices).  Step j needs one barrier: every thread publishes its still-unscaled a[r][j],
+// then updates its row with a[r][c] -= a[r][j] a[c][j] / d_j (no sqrt on the critical path;
+// the 1/sqrt(d_j) scaling of column j happens on the side).  The inverse is computed column
+// per thread against L broadcast from shared memory, with no barrier at all.
+__global__ void __launch_bounds__(64)
 chol_diag(double *__restrict__ S, int ld, int k0, int kb, double *__restrict__ linv_out,
           double *__restrict__ fail) {
-    extern __shared__ __align__(16) double smem_d[];
-    double(*A)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d);
-    double(*Li)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d + NB * (NB + 1));
-    double *Ld = smem_d + 2 * NB * (NB + 1);
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int r = idx >> 6, c = idx & 63;
-        A[r][c] = (r < kb && c <= r) ? S[(size_t)(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
-        Li[r][c] = 0.0;
-    }
-    __syncthreads();
-    const int r = tid >> 2, sub = tid & 3;
-    for (int j = 0; j < kb; ++j) {
-        double d = A[j][j];
-        if (!(d > 0.0) || !isfinite(d)) {
-            if (tid == 0) *fail = 1.0;
-            d = 1.0;
-        }
-        const double l = sqrt(d), inv = 1.0 / l;
-        if (tid == j) Ld[j] = l;
-        if (tid > j && tid < kb) A[tid][j] *= inv;
+    __shared__ double Ls[NB][NB + 1];
+    __shared__ double col[2][NB];
+    const int r = threadIdx.x;
+    double a[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+        a[c] = (r < kb && c <= r && c < kb) ? S[(size_t)(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        col[j & 1][r] = a[j];
         __syncthreads();
-        if (r > j && r < kb) {
-            const double arj = A[r][j];
-            for (int c = j + 1 + sub; c <= r; c += 4) A[r][c] -= arj * A[c][j];
-        }
-        __syncthreads();
+        double d = col[j & 1][j];
+        if (!(d > 0.0) || !isfinite(d)) bad = true, d = 1.0;
+        const double t = a[j] / d;
+#pragma unroll
+        for (int c = j + 1; c < NB; ++c)
+            if (c <= r) a[c] = fma(-t, col[j & 1][c], a[c]);
+        a[j] = a[j] / sqrt(d);  // final L[r][j] (r >= j)
     }
-    if (tid < kb) A[tid][tid] = Ld[tid];
+    if (bad && r == 0) *fail = 1.0;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) Ls[r][c] = c <= r ? a[c] : 0.0;
     __syncthreads();
-    // Linv = L^-1: column c by forward substitution, 4 lanes share the inner products
-    {
-        const int c = tid >> 2;  // 64 columns x 4 lanes; every lane walks all rows (shuffles
-        for (int rr = 0; rr < kb; ++rr) {  // need the whole warp), rows above the diagonal idle
-            double v = 0.0;
-            if (rr >= c)
-                for (int p = c + sub; p < rr; p += 4) v += A[rr][p] * Li[p][c];
-            v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
-            v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
-            if (sub == 0 && c < kb && rr >= c) Li[rr][c] = ((rr == c ? 1.0 : 0.0) - v) / A[rr][rr];
-            __syncwarp();
-        }
+    // write L back (lower part of the real rows)
+    if (r < kb)
+#pragma unroll 8
+        for (int c = 0; c <= r; ++c) S[(size_t)(k0 + r) * ld + k0 + c] = Ls[r][c];
+    // column c = threadIdx.x of X = L^-1:  X[rr][c] = (delta - sum_{p<rr} L[rr][p] X[p][c]) / L[rr][rr]
+    double x[NB];
+#pragma unroll
+    for (int rr = 0; rr < NB; ++rr) {
+        double v = rr == r ? 1.0 : 0.0;
+#pragma unroll
+        for (int p = 0; p < rr; ++p) v = fma(-Ls[rr][p], x[p], v);
+        x[rr] = v / Ls[rr][rr];
     }
-    __syncthreads();
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int rr = idx >> 6, c = idx & 63;
-        if (rr < kb && c <= rr) S[(size_t)(k0 + rr) * ld + k0 + c] = A[rr][c];
-        linv_out[idx] = (rr < kb && c < kb) ? Li[rr][c] : 0.0;
-    }
+#pragma unroll
+    for (int rr = 0; rr < NB; ++rr) linv_out[rr * NB + r] = (rr < kb && r < kb) ? x[rr] : 0.0;
 }
 
 // ---- FP64 GEMM tile: acc[i][j] = sum_p X[row(ty,i)][p] * Y[col(tx,j)][p], p < 64 -------------
@@ -228,7 +222,7 @@ int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, d
     for (int kblk = 0; kblk < nblk; ++kblk) {
         const int k0 = kblk * NB, kb = min(NB, n - k0);
         double *li = linv + (size_t)kblk * NB * NB;
-        chol_diag<<<1, 256, kDiagSmem, st>>>(S, ld, k0, kb, li, fail_flag);
+        chol_diag<<<1, 64, 0, st>>>(S, ld, k0, kb, li, fail_flag);
         const int r0 = k0 + kb;
         const int r1 = min(n, r0 + bw);  // rows that can be non-zero in this block column
         const int np = (r1 - r0 + 127) / 128;
@@ -272,7 +266,6 @@ int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, dou
     if (n <= 0) return XRB_OK;
     static bool attr_set = false;
     if (!attr_set) {
-        XRB_CUDA(cudaFuncSetAttribute(chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
         XRB_CUDA(cudaFuncSetAttribute(chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Tile<128, 64>::kSmemBytes));
         XRB_CUDA(cudaFuncSetAttribute(chol_update<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -38,11 +38,12 @@ constexpr int kThreads = 32 * 10;
 //         memory as one packed 64-bit word per row/column, candidates go through per-warp
 //         queues, and thresholds + mutual test + ordered compaction run in the same kernel.
 constexpr int kFusedMax = 4096;
+constexpr int kLaneQueue = 4;  // candidates a lane can park before the warp drains
 template <bool kFused> struct Cfg {
     static constexpr int kGroupN = kFused ? 768 : 1024;  // resident B descriptors per group
     static constexpr int kBGroupBytes = kGroupN * kDim;
     static constexpr int kStateBytes = kFused ? 2 * kFusedMax * 8 : 0;
-    static constexpr int kQueueBytes = kFused ? 8 * 64 * 8 : 0;
+    static constexpr int kQueueBytes = kFused ? 8 * kLaneQueue * 32 * 8 : 0;
     static constexpr int kSmemBytes = kBGroupBytes + kAStages * kATileBytes + kStateBytes + kQueueBytes +
                                       1024 /*align*/ + 256 /*barriers*/;
 };
@@ -118,6 +119,19 @@ __device__ __forceinline__ void push_top2(unsigned long long *best, unsigned int
     if (lv) atomicMax(second, lv);
 }
 
+// 32 lanes x 32 consecutive TMEM columns -> 32 registers per thread
+__device__ __forceinline__ void ldtm32(uint32_t taddr, int *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
 struct Bars {
     unsigned long long b_full, b_empty;
     unsigned long long a_full[kAStages], a_empty[kAStages];
@@ -170,7 +184,7 @@ __device__ __forceinline__ bool accept_tab(const float *__restrict__ tab, uint32
 }
 
 template <bool kFused>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(200)
 score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const uint8_t *baseA, const uint8_t *baseB, const PairDesc *__restrict__ pairs,
                 int n_pairs, int state_stride, Top2State rows, Top2State cols,
@@ -279,26 +293,36 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int quarter = warp & 3;       // TMEM lane quarter this warp may touch (warp id % 4)
         const int half = ew >> 2;           // which 128-column half of the 256-column tile
         const int vlow = *vlow_ptr;
-        unsigned long long *q = queues + ew * 64;
-        int qn = 0;                          // warp-uniform queue fill
-        const unsigned lt_mask = (1u << lane) - 1u;
+        // per-lane private candidate queues: q[slot][lane]; no coordination needed to append
+        unsigned long long *q = queues + ew * (kLaneQueue * 32) + lane;
+        int qn = 0;  // this lane's fill
         uint32_t t_it = 0;
         if (kFused) {
             for (int z = et; z < 2 * kFusedMax; z += 256) st_rows[z] = 0ull;
             epi_bar();
         }
+        auto apply = [&](uint32_t val, uint32_t ii, uint32_t jj) {
+            top2_update(st_rows + ii, val, 8191u - rank13_row(jj));
+            top2_update(st_cols + jj, val, 8191u - ii);
+        };
         auto drain = [&]() {
-            __syncwarp();
-            for (int b0 = 0; b0 < qn; b0 += 32) {
-                if (b0 + lane < qn) {
-                    const unsigned long long e = q[b0 + lane];
-                    const uint32_t v = (uint32_t)(e >> 26), i = (uint32_t)(e >> 13) & 0x1FFFu, j = (uint32_t)e & 0x1FFFu;
-                    top2_update(st_rows + i, v, 8191u - rank13_row(j));
-                    top2_update(st_cols + j, v, 8191u - i);
+            for (int k = 0; k < kLaneQueue; ++k)
+                if (k < qn) {
+                    const unsigned long long e = q[k * 32];
+                    apply((uint32_t)(e >> 26), (uint32_t)(e >> 13) & 0x1FFFu, (uint32_t)e & 0x1FFFu);
                 }
-            }
-            __syncwarp();
             qn = 0;
+            __syncwarp();
+        };
+        // a candidate found by this lane: park it, or (queue full: dense/adversarial input) apply now
+        auto park = [&](int val, int ii, int jj) {
+            if (qn < kLaneQueue) {
+                q[qn * 32] = ((unsigned long long)(unsigned)val << 26) | ((unsigned long long)(unsigned)ii << 13) |
+                             (unsigned)jj;
+                ++qn;
+            } else {
+                apply((uint32_t)val, (uint32_t)ii, (uint32_t)jj);
+            }
         };
         for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
             const PairDesc pd = pairs[p];
@@ -319,66 +343,55 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         tc_fence_after();
                         const int col_tile = g0 + ns * kTileN + half * 128;
                         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + tb * kTileN + half * 128;
-#pragma unroll 1
-                        for (int ch = 0; ch < 4; ++ch) {
-                            int v[32];
-                            asm volatile(
-                                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-                                  "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-                                  "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
-                                  "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
-                                  "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                                : "r"(taddr + ch * 32));
-                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                            if (ch == 3) {  // accumulator fully read: hand the TMEM buffer back
-                                tc_fence_before();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(smem_u32(&bars->t_empty[tb]));
-                            }
-                            const int j0 = col_tile + ch * 32;
+                        // all 128 columns of this warp's slice in flight at once (4 x 32x32b.x32),
+                        // one wait, then the TMEM buffer goes back to the MMA warp while the
+                        // registers are filtered: the load latency overlaps with the other
+                        // epilogue warp of the same scheduler instead of serialising per chunk
+                        int v[128];
+                        ldtm32(taddr, v);
+                        ldtm32(taddr + 32, v + 32);
+                        ldtm32(taddr + 64, v + 64);
+                        ldtm32(taddr + 96, v + 96);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&bars->t_empty[tb]));
 #pragma unroll
-                            for (int g = 0; g < 32; g += 16) {
-                                int mx = v[g];
+                        for (int g = 0; g < 128; g += 16) {
+                            const int j0 = col_tile + g;
+                            int mx = v[g];
 #pragma unroll
-                                for (int e = 1; e < 16; ++e) mx = max(mx, v[g + e]);
-                                if (kFused) {
-                                    // warp-uniform slow path: candidates are appended to the warp's
-                                    // queue with ballot-derived slots (no atomics), drained 32 at a time
-                                    if (__any_sync(0xFFFFFFFFu, mx > vlow && i < pd.n1)) {
+                            for (int e = 1; e < 16; ++e) mx = max(mx, v[g + e]);
+                            if (kFused) {
+                                // lane-divergent slow path (a few % of the lanes): descend by quarters
+                                // of the group, park the hits in the lane's own queue
+                                if (mx > vlow && i < pd.n1) {
 #pragma unroll
-                                        for (int e = 0; e < 16; ++e) {
-                                            const int val = v[g + e], j = j0 + g + e;
-                                            const bool c = val > vlow && i < pd.n1 && j < pd.n2;
-                                            const unsigned mk = __ballot_sync(0xFFFFFFFFu, c);
-                                            if (mk) {
-                                                if (c)
-                                                    q[qn + __popc(mk & lt_mask)] =
-                                                        ((unsigned long long)(unsigned)val << 26) |
-                                                        ((unsigned long long)(unsigned)i << 13) | (unsigned)j;
-                                                qn += __popc(mk);
-                                                if (qn > 32) drain();
-                                            }
-                                        }
-                                    }
-                                } else if (mx > vlow && i < pd.n1) {
+                                    for (int qd = 0; qd < 16; qd += 4) {
+                                        const int mq = max(max(v[g + qd], v[g + qd + 1]), max(v[g + qd + 2], v[g + qd + 3]));
+                                        if (mq > vlow) {
 #pragma unroll
-                                    for (int e = 0; e < 16; ++e) {
-                                        const int val = v[g + e], j = j0 + g + e;
-                                        if (val > vlow && j < pd.n2) {
-                                            const unsigned long long hv = (unsigned long long)(unsigned int)val << 32;
-                                            push_top2(rows.best + sbase + i, rows.second + sbase + i,
-                                                      hv | (0xFFFFFFFFu - row_tie_rank((uint32_t)j)));
-                                            push_top2(cols.best + sbase + j, cols.second + sbase + j,
-                                                      hv | (0xFFFFFFFFu - (uint32_t)i));
+                                            for (int e = qd; e < qd + 4; ++e)
+                                                if (v[g + e] > vlow && j0 + e < pd.n2) park(v[g + e], i, j0 + e);
                                         }
                                     }
                                 }
+                            } else if (mx > vlow && i < pd.n1) {
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) {
+                                    const int val = v[g + e], j = j0 + e;
+                                    if (val > vlow && j < pd.n2) {
+                                        const unsigned long long hv = (unsigned long long)(unsigned int)val << 32;
+                                        push_top2(rows.best + sbase + i, rows.second + sbase + i,
+                                                  hv | (0xFFFFFFFFu - row_tie_rank((uint32_t)j)));
+                                        push_top2(cols.best + sbase + j, cols.second + sbase + j,
+                                                  hv | (0xFFFFFFFFu - (uint32_t)i));
+                                    }
+                                }
                             }
-                            __syncwarp();  // reconverge before the next .aligned tcgen05.ld
                         }
+                        __syncwarp();  // reconverge before the next .aligned tcgen05.ld
+                        if (kFused && __any_sync(0xFFFFFFFFu, qn >= kLaneQueue - 1)) drain();
                     }
                 }
             }
@@ -418,7 +431,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         before += w < ew ? c : 0;
                         total += c;
                     }
-                    const int pos = running + before + __popc(ballot & lt_mask);
+                    const int pos = running + before + __popc(ballot & ((1u << lane) - 1u));
                     if (flag && pos < fa.max_match) dst[pos][0] = (uint32_t)r, dst[pos][1] = (uint32_t)j;
                     running += total;
                     epi_bar();
