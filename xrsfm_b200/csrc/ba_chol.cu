@@ -87,18 +87,30 @@ struct Tile {
     template <int T>
     __device__ static void stage(double *dst, int ldd, const double *__restrict__ src, size_t ld, int nrows,
                                  int kb) {
-        for (int idx = threadIdx.x; idx < T * (NB / 2); idx += 256) {
-            const int row = idx >> 5, p = (idx & 31) * 2;
-            double2 v = make_double2(0.0, 0.0);
-            if (row < nrows) {
-                const double *g = src + (size_t)row * ld + p;
-                if (p + 1 < kb)
-                    v = *reinterpret_cast<const double2 *>(g);
-                else if (p < kb)
-                    v.x = g[0];
+        // 8 independent 16-byte loads in flight per thread before any shared-memory store:
+        // the tile staging is latency-bound otherwise (one L2 round trip per element pair)
+        constexpr int kBatch = 8;
+        static_assert((T * (NB / 2)) % (256 * kBatch) == 0, "tile must be a multiple of the batch");
+        for (int base = threadIdx.x; base < T * (NB / 2); base += 256 * kBatch) {
+            double2 v[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int idx = base + u * 256, row = idx >> 5, p = (idx & 31) * 2;
+                v[u] = make_double2(0.0, 0.0);
+                if (row < nrows) {
+                    const double *g = src + (size_t)row * ld + p;
+                    if (p + 1 < kb)
+                        v[u] = __ldg(reinterpret_cast<const double2 *>(g));
+                    else if (p < kb)
+                        v[u].x = __ldg(g);
+                }
             }
-            dst[p * ldd + row] = v.x;
-            dst[(p + 1) * ldd + row] = v.y;
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int idx = base + u * 256, row = idx >> 5, p = (idx & 31) * 2;
+                dst[p * ldd + row] = v[u].x;
+                dst[(p + 1) * ldd + row] = v[u].y;
+            }
         }
     }
 

@@ -165,6 +165,44 @@ __device__ __forceinline__ void top2_update(unsigned long long *addr, uint32_t v
     } while (old != assumed);
 }
 
+// Out-of-line slow path of the fused epilogue (keeps the hot loop small enough for the
+// instruction cache): one lane found a group of 16 accumulators whose maximum exceeds v_low.
+// Hits are parked in the lane's private queue q[slot * 32]; a full queue applies directly.
+__device__ __noinline__ int fused_slow16(int qn, unsigned long long *q, unsigned long long *st_rows,
+                                         unsigned long long *st_cols, int vlow, int i, int j0, int n2, int4 a,
+                                         int4 b, int4 c, int4 d) {
+    const int v[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        if (v[e] > vlow && j0 + e < n2) {
+            if (qn < kLaneQueue) {
+                q[qn * 32] = ((unsigned long long)(unsigned)v[e] << 26) | ((unsigned long long)(unsigned)i << 13) |
+                             (unsigned)(j0 + e);
+                ++qn;
+            } else {
+                top2_update(st_rows + i, (uint32_t)v[e], 8191u - rank13_row((uint32_t)(j0 + e)));
+                top2_update(st_cols + j0 + e, (uint32_t)v[e], 8191u - (uint32_t)i);
+            }
+        }
+    }
+    return qn;
+}
+
+// Same for the global-state flavour: lock-free pushes into the per-row / per-column state.
+__device__ __noinline__ void global_slow16(Top2State rows, Top2State cols, size_t sbase, int vlow, int i, int j0,
+                                           int n2, int4 a, int4 b, int4 c, int4 d) {
+    const int v[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        const int j = j0 + e;
+        if (v[e] > vlow && j < n2) {
+            const unsigned long long hv = (unsigned long long)(unsigned int)v[e] << 32;
+            push_top2(rows.best + sbase + i, rows.second + sbase + i, hv | (0xFFFFFFFFu - row_tie_rank((uint32_t)j)));
+            push_top2(cols.best + sbase + j, cols.second + sbase + j, hv | (0xFFFFFFFFu - (uint32_t)i));
+        }
+    }
+}
+
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 struct FusedArgs {
@@ -184,7 +222,7 @@ __device__ __forceinline__ bool accept_tab(const float *__restrict__ tab, uint32
 }
 
 template <bool kFused>
-__global__ void __maxnreg__(200)
+__global__ void __maxnreg__(192)
 score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const uint8_t *baseA, const uint8_t *baseB, const PairDesc *__restrict__ pairs,
                 int n_pairs, int state_stride, Top2State rows, Top2State cols,
@@ -365,29 +403,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             if (kFused) {
                                 // lane-divergent slow path (a few % of the lanes): descend by quarters
                                 // of the group, park the hits in the lane's own queue
-                                if (mx > vlow && i < pd.n1) {
-#pragma unroll
-                                    for (int qd = 0; qd < 16; qd += 4) {
-                                        const int mq = max(max(v[g + qd], v[g + qd + 1]), max(v[g + qd + 2], v[g + qd + 3]));
-                                        if (mq > vlow) {
-#pragma unroll
-                                            for (int e = qd; e < qd + 4; ++e)
-                                                if (v[g + e] > vlow && j0 + e < pd.n2) park(v[g + e], i, j0 + e);
-                                        }
-                                    }
-                                }
+                                if (mx > vlow && i < pd.n1)
+                                    qn = fused_slow16(qn, q, st_rows, st_cols, vlow, i, j0, pd.n2,
+                                                      make_int4(v[g], v[g + 1], v[g + 2], v[g + 3]),
+                                                      make_int4(v[g + 4], v[g + 5], v[g + 6], v[g + 7]),
+                                                      make_int4(v[g + 8], v[g + 9], v[g + 10], v[g + 11]),
+                                                      make_int4(v[g + 12], v[g + 13], v[g + 14], v[g + 15]));
                             } else if (mx > vlow && i < pd.n1) {
-#pragma unroll
-                                for (int e = 0; e < 16; ++e) {
-                                    const int val = v[g + e], j = j0 + e;
-                                    if (val > vlow && j < pd.n2) {
-                                        const unsigned long long hv = (unsigned long long)(unsigned int)val << 32;
-                                        push_top2(rows.best + sbase + i, rows.second + sbase + i,
-                                                  hv | (0xFFFFFFFFu - row_tie_rank((uint32_t)j)));
-                                        push_top2(cols.best + sbase + j, cols.second + sbase + j,
-                                                  hv | (0xFFFFFFFFu - (uint32_t)i));
-                                    }
-                                }
+                                global_slow16(rows, cols, sbase, vlow, i, j0, pd.n2,
+                                              make_int4(v[g], v[g + 1], v[g + 2], v[g + 3]),
+                                              make_int4(v[g + 4], v[g + 5], v[g + 6], v[g + 7]),
+                                              make_int4(v[g + 8], v[g + 9], v[g + 10], v[g + 11]),
+                                              make_int4(v[g + 12], v[g + 13], v[g + 14], v[g + 15]));
                             }
                         }
                         __syncwarp();  // reconverge before the next .aligned tcgen05.ld
