@@ -241,6 +241,12 @@ int xrb_ba_residuals(xrb_ba_solver *s, double *out_residuals);
  * [5] whole run; and launches of each (same indices). */
 int xrb_ba_profile(const xrb_ba_solver *s, double ms[6], int64_t launches[6]);
 
+/* Finer split of the last run, out[n >= 8]: [0..2] total ms of k_lin (+ memsets), k_gather,
+ * k_cam_blocks; [3] linear solves executed; [4] off-diagonal 6x6 blocks of the reduced camera
+ * system; [5] (block, point) incidences the gather walks; [6] reduced system dimension;
+ * [7] its half bandwidth. */
+int xrb_ba_profile_detail(const xrb_ba_solver *s, double *out, int n);
+
 #ifdef __cplusplus
 }
 #endif

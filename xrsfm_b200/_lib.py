@@ -93,6 +93,7 @@ SIGNATURES = {
     "xrb_ba_fetch": (C.c_int, [C.c_void_p, C.POINTER(BAProblem)]),
     "xrb_ba_residuals": (C.c_int, [C.c_void_p, C.c_void_p]),
     "xrb_ba_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xrb_ba_profile_detail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
 }
 
 

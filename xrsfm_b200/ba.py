@@ -152,6 +152,12 @@ class BASolver:
         names = ("schur", "solve", "backsub", "cost", "exchange", "run")
         return {n: (ms[i], ln[i]) for i, n in enumerate(names)}
 
+    def profile_detail(self):
+        out = (C.c_double * 8)()
+        _lib.check(_lib.lib().xrb_ba_profile_detail(self._h, out, 8), "xrb_ba_profile_detail")
+        keys = ("lin_ms", "gather_ms", "cam_blocks_ms", "solves", "n_blocks", "n_incidences", "nc", "half_bandwidth")
+        return dict(zip(keys, list(out)))
+
     def set_exchange(self, rank, world, allreduce):
         """allreduce(ptr: int, count: int) -> None: in-place SUM over ranks of `count` doubles
         at device address `ptr` (see include/xrsfm_b200.h xrb_ba_set_exchange)."""

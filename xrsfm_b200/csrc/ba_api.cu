@@ -62,6 +62,8 @@ struct xrb_ba_solver {
 
     double ms[6] = {0, 0, 0, 0, 0, 0};
     int64_t launches[6] = {0, 0, 0, 0, 0, 0};
+    double ms_kernel[3] = {0, 0, 0};  // generation-2 Schur split: k_lin, k_gather, k_cam_blocks
+    int64_t n_steps = 0;              // compute_step calls of the last run
 
     BAProblemDev prob() const {
         BAProblemDev p;
@@ -305,7 +307,7 @@ struct StepOut {
 
 // One linear solve + candidate evaluation from the state in slot `cur`; candidate in slot 1-cur.
 int compute_step(xrb_ba_solver *s, const BAConsts &k, double radius, cudaStream_t st, StepOut &out,
-                 Ev ev[8]) {
+                 Ev ev[10]) {
     const BAProblemDev P = s->prob();
     const BALinSys L = s->linsys();
     const BAStateDev x = s->state(s->cur), cand = s->state(1 - s->cur);
@@ -318,7 +320,9 @@ int compute_step(xrb_ba_solver *s, const BAConsts &k, double radius, cudaStream_
     XRB_CUDA(cudaMemsetAsync(s->d_scal.p, 0, 2 * SC_COUNT * 8, st));
     if (s->schur_gen == 2) {
         if ((rc = ba_launch_lin(P, x, k, L, inv_radius, s->scalE(), st))) return rc;
+        ev[7].rec(st);
         if ((rc = ba_launch_gather(P, L, st))) return rc;
+        ev[8].rec(st);
         if ((rc = ba_launch_cam_blocks(P, x, k, L, st))) return rc;
         s->launches[0] += 3;
     } else {
@@ -366,6 +370,13 @@ int compute_step(xrb_ba_solver *s, const BAConsts &k, double radius, cudaStream_
     out.ok = hE[SC_FAIL] == 0.0 && h2[SC_FAIL] == 0.0 && hL[SC_FAIL] == 0.0 && std::isfinite(out.model_cost_change) &&
              std::isfinite(out.cand_cost) && std::isfinite(out.step_norm);
     // phase timings
+    s->n_steps++;
+    if (s->schur_gen == 2) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ev[0].e, ev[7].e) == cudaSuccess) s->ms_kernel[0] += t;  // memsets + k_lin
+        if (cudaEventElapsedTime(&t, ev[7].e, ev[8].e) == cudaSuccess) s->ms_kernel[1] += t;
+        if (cudaEventElapsedTime(&t, ev[8].e, ev[1].e) == cudaSuccess) s->ms_kernel[2] += t;
+    }
     static const int phase_of[6] = {0, 4, 1, 2, 3, 4};
     for (int i = 0; i < 6; ++i) {
         float t = 0.f;
@@ -395,11 +406,12 @@ int do_run(xrb_ba_solver *s, const xrb_ba_options *O, xrb_ba_summary *sum, cudaS
     const auto t0 = std::chrono::steady_clock::now();
     memset(sum, 0, sizeof *sum);
     for (int i = 0; i < 6; ++i) s->ms[i] = 0.0, s->launches[i] = 0;
+    s->ms_kernel[0] = s->ms_kernel[1] = s->ms_kernel[2] = 0.0, s->n_steps = 0;
     BAConsts k{O->huber_a, O->huber_a * O->huber_a, O->min_depth, O->neg_depth_residual};
     sum->num_residuals_reduced = 2 * s->n_res_blocks;
     sum->num_effective_parameters_reduced = 3 * (s->n_var_q + s->n_var_t + s->n_var_pts);
     sum->termination_type = XRB_BA_NO_CONVERGENCE;
-    Ev ev[8], ev_run[2];
+    Ev ev[10], ev_run[2];
     ev_run[0].rec(st);
     int rc;
     double fixed_cost = 0.0, x_cost = 0.0;
@@ -712,6 +724,14 @@ int xrb_ba_residuals(xrb_ba_solver *s, double *out) {
     cudaStreamSynchronize(st);
     tmp.release();
     return rc;
+}
+
+int xrb_ba_profile_detail(const xrb_ba_solver *s, double *out, int n) {
+    if (!s || !out || n < 8) return XRB_ERR_INVALID;
+    out[0] = s->ms_kernel[0], out[1] = s->ms_kernel[1], out[2] = s->ms_kernel[2];
+    out[3] = (double)s->n_steps, out[4] = (double)s->n_blocks, out[5] = (double)s->n_inc;
+    out[6] = (double)s->nc, out[7] = (double)s->bw;
+    return XRB_OK;
 }
 
 int xrb_ba_profile(const xrb_ba_solver *s, double ms[6], int64_t launches[6]) {
