@@ -23,53 +23,125 @@ namespace xrb {
 constexpr int NB = 64;  // block-column width == GEMM depth
 
 // ---- 1. diagonal block ---------------------------------------------------------------------
-// 64 threads, thread r keeps row r of the block in registers (fully unrolled, static
-// indices).  Step j needs one barrier: every thread publishes its still-unscaled a[r][j],
-// then updates its row with a[r][c] -= a[r][j] a[c][j] / d_j (no sqrt on the critical path;
-// the 1/sqrt(d_j) scaling of column j happens on the side).  The inverse is computed column
-// per thread against L broadcast from shared memory, with no barrier at all.
-__global__ void __launch_bounds__(64)
+// 64 x 64 Cholesky + inverse in one CTA (256 threads), blocked by 16:
+//   for each 16-block: warp 0 factors the 16 x 16 diagonal sub-block and inverts it entirely
+//   in registers (row per lane, values exchanged by shuffles); all warps then form the panel
+//   below it (multiply by the 16 x 16 inverse) and apply the rank-16 trailing update.
+//   Finally the off-diagonal 16-blocks of L^-1 are filled block-diagonal by block-diagonal:
+//   X_ij = -X_ii (sum_k L_ik X_kj).
+// ~13 barriers in total instead of 128 (one per column) in the unblocked form.
+constexpr int SB = 16;
+constexpr int kDiagSmem = (2 * NB * (NB + 1) + NB * (SB + 1)) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256)
 chol_diag(double *__restrict__ S, int ld, int k0, int kb, double *__restrict__ linv_out,
           double *__restrict__ fail) {
-    __shared__ double Ls[NB][NB + 1];
-    __shared__ double col[2][NB];
-    const int r = threadIdx.x;
-    double a[NB];
-#pragma unroll
-    for (int c = 0; c < NB; ++c)
-        a[c] = (r < kb && c <= r && c < kb) ? S[(size_t)(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
-    bool bad = false;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-        col[j & 1][r] = a[j];
-        __syncthreads();
-        double d = col[j & 1][j];
-        if (!(d > 0.0) || !isfinite(d)) bad = true, d = 1.0;
-        const double t = a[j] / d;
-#pragma unroll
-        for (int c = j + 1; c < NB; ++c)
-            if (c <= r) a[c] = fma(-t, col[j & 1][c], a[c]);
-        a[j] = a[j] / sqrt(d);  // final L[r][j] (r >= j)
+    extern __shared__ __align__(16) double smem_d[];
+    double(*A)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d);                      // L when done
+    double(*X)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d + NB * (NB + 1));      // L^-1
+    double(*T)[SB + 1] = reinterpret_cast<double(*)[SB + 1]>(smem_d + 2 * NB * (NB + 1));  // scratch
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int r = idx >> 6, c = idx & 63;
+        A[r][c] = (r < kb && c <= r) ? S[(size_t)(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
+        X[r][c] = 0.0;
     }
-    if (bad && r == 0) *fail = 1.0;
-#pragma unroll
-    for (int c = 0; c < NB; ++c) Ls[r][c] = c <= r ? a[c] : 0.0;
     __syncthreads();
-    // write L back (lower part of the real rows)
-    if (r < kb)
-#pragma unroll 8
-        for (int c = 0; c <= r; ++c) S[(size_t)(k0 + r) * ld + k0 + c] = Ls[r][c];
-    // column c = threadIdx.x of X = L^-1:  X[rr][c] = (delta - sum_{p<rr} L[rr][p] X[p][c]) / L[rr][rr]
-    double x[NB];
+    bool bad = false;
+    for (int b = 0; b < NB; b += SB) {
+        if (warp == 0) {
+            // ---- 16 x 16 factor: lane l (< 16) owns row b + l
+            const int rl = lane & 15;
+            double a[SB];
 #pragma unroll
-    for (int rr = 0; rr < NB; ++rr) {
-        double v = rr == r ? 1.0 : 0.0;
+            for (int c = 0; c < SB; ++c) a[c] = A[b + rl][b + c];
 #pragma unroll
-        for (int p = 0; p < rr; ++p) v = fma(-Ls[rr][p], x[p], v);
-        x[rr] = v / Ls[rr][rr];
+            for (int j = 0; j < SB; ++j) {
+                double d = __shfl_sync(0xFFFFFFFFu, a[j], j);
+                if (!(d > 0.0) || !isfinite(d)) bad = true, d = 1.0;
+                const double ljj = sqrt(d);
+                a[j] = rl == j ? ljj : a[j] / ljj;  // L[r][j] for r >= j
+#pragma unroll
+                for (int c = j + 1; c < SB; ++c) {
+                    const double lcj = __shfl_sync(0xFFFFFFFFu, a[j], c);
+                    if (rl >= c) a[c] = fma(-a[j], lcj, a[c]);
+                }
+            }
+            // ---- its inverse: lane l owns column l; L[r][p] broadcast from lane r
+            double x[SB];
+#pragma unroll
+            for (int r = 0; r < SB; ++r) {
+                double v = rl == r ? 1.0 : 0.0;
+#pragma unroll
+                for (int p = 0; p < r; ++p) v = fma(-__shfl_sync(0xFFFFFFFFu, a[p], r), x[p], v);
+                x[r] = v / __shfl_sync(0xFFFFFFFFu, a[r], r);
+            }
+            if (lane < SB) {
+#pragma unroll
+                for (int c = 0; c < SB; ++c) {
+                    if (c <= rl) A[b + rl][b + c] = a[c];
+                    X[b + c][b + rl] = c >= rl ? x[c] : 0.0;  // x[c] = X[c][column rl]
+                }
+            }
+        }
+        __syncthreads();
+        const int below = NB - b - SB;  // rows under the sub-block
+        if (below > 0) {
+            // ---- panel: P[i][c] = sum_{p <= c} A[i][b+p] * Xbb[c][p]   (= A_panel * Lbb^-T)
+            for (int idx = tid; idx < below * SB; idx += 256) {
+                const int i = b + SB + (idx >> 4), c = idx & 15;
+                double v = 0.0;
+#pragma unroll
+                for (int p = 0; p < SB; ++p)
+                    if (p <= c) v = fma(A[i][b + p], X[b + c][b + p], v);
+                T[i][c] = v;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < below * SB; idx += 256) {
+                const int i = b + SB + (idx >> 4), c = idx & 15;
+                A[i][b + c] = T[i][c];
+            }
+            __syncthreads();
+            // ---- trailing update: A[i][j] -= sum_p A[i][b+p] A[j][b+p], j <= i
+            for (int idx = tid; idx < below * below; idx += 256) {
+                const int i = b + SB + idx / below, j = b + SB + idx % below;
+                if (j > i) continue;
+                double v = 0.0;
+#pragma unroll
+                for (int p = 0; p < SB; ++p) v = fma(A[i][b + p], A[j][b + p], v);
+                A[i][j] -= v;
+            }
+            __syncthreads();
+        }
     }
+    if (bad && lane == 0) *fail = 1.0;
+    // ---- off-diagonal 16-blocks of X = L^-1, by block distance d: X_ij = -X_ii * sum_k L_ik X_kj
+    for (int d = 1; d < NB / SB; ++d) {
+        const int nblk = NB / SB - d;  // blocks (i, j = i - d), i = d .. 3
+        for (int idx = tid; idx < nblk * SB * SB; idx += 256) {
+            const int bi = d + idx / (SB * SB), r = (idx >> 4) & 15, c = idx & 15, bj = bi - d;
+            double v = 0.0;
+            for (int k = bj; k < bi; ++k)
 #pragma unroll
-    for (int rr = 0; rr < NB; ++rr) linv_out[rr * NB + r] = (rr < kb && r < kb) ? x[rr] : 0.0;
+                for (int p = 0; p < SB; ++p) v = fma(A[bi * SB + r][k * SB + p], X[k * SB + p][bj * SB + c], v);
+            T[(bi - d) * SB + r][c] = v;  // one 16-row slab of T per block of this distance
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nblk * SB * SB; idx += 256) {
+            const int bi = d + idx / (SB * SB), r = (idx >> 4) & 15, c = idx & 15, bj = bi - d;
+            double v = 0.0;
+#pragma unroll
+            for (int p = 0; p < SB; ++p)
+                if (p <= r) v = fma(X[bi * SB + r][bi * SB + p], T[(bi - d) * SB + p][c], v);
+            X[bi * SB + r][bj * SB + c] = -v;
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int r = idx >> 6, c = idx & 63;
+        if (r < kb && c <= r) S[(size_t)(k0 + r) * ld + k0 + c] = A[r][c];
+        linv_out[idx] = (r < kb && c < kb) ? X[r][c] : 0.0;
+    }
 }
 
 // ---- FP64 GEMM tile: acc[i][j] = sum_p X[row(ty,i)][p] * Y[col(tx,j)][p], p < 64 -------------
@@ -234,7 +306,7 @@ int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, d
     for (int kblk = 0; kblk < nblk; ++kblk) {
         const int k0 = kblk * NB, kb = min(NB, n - k0);
         double *li = linv + (size_t)kblk * NB * NB;
-        chol_diag<<<1, 64, 0, st>>>(S, ld, k0, kb, li, fail_flag);
+        chol_diag<<<1, 256, kDiagSmem, st>>>(S, ld, k0, kb, li, fail_flag);
         const int r0 = k0 + kb;
         const int r1 = min(n, r0 + bw);  // rows that can be non-zero in this block column
         const int np = (r1 - r0 + 127) / 128;
@@ -278,6 +350,7 @@ int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, dou
     if (n <= 0) return XRB_OK;
     static bool attr_set = false;
     if (!attr_set) {
+        XRB_CUDA(cudaFuncSetAttribute(chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
         XRB_CUDA(cudaFuncSetAttribute(chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Tile<128, 64>::kSmemBytes));
         XRB_CUDA(cudaFuncSetAttribute(chol_update<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,

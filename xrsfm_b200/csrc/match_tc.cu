@@ -222,7 +222,7 @@ __device__ __forceinline__ bool accept_tab(const float *__restrict__ tab, uint32
 }
 
 template <bool kFused>
-__global__ void __maxnreg__(192)
+__global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const uint8_t *baseA, const uint8_t *baseB, const PairDesc *__restrict__ pairs,
                 int n_pairs, int state_stride, Top2State rows, Top2State cols,
@@ -381,22 +381,23 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         tc_fence_after();
                         const int col_tile = g0 + ns * kTileN + half * 128;
                         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + tb * kTileN + half * 128;
-                        // all 128 columns of this warp's slice in flight at once (4 x 32x32b.x32),
-                        // one wait, then the TMEM buffer goes back to the MMA warp while the
-                        // registers are filtered: the load latency overlaps with the other
-                        // epilogue warp of the same scheduler instead of serialising per chunk
-                        int v[128];
-                        ldtm32(taddr, v);
-                        ldtm32(taddr + 32, v + 32);
-                        ldtm32(taddr + 64, v + 64);
-                        ldtm32(taddr + 96, v + 96);
+                        // 64 columns (2 x 32x32b.x32) in flight per wait: the register file of an
+                        // SM sub-partition (16 K) holds 3 of the CTA's 10 warps, which caps a thread
+                        // at 168 registers — 128 accumulators in flight would spill
+#pragma unroll 1
+                        for (int hh = 0; hh < 2; ++hh) {
+                        int v[64];
+                        ldtm32(taddr + hh * 64, v);
+                        ldtm32(taddr + hh * 64 + 32, v + 32);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&bars->t_empty[tb]));
+                        if (hh == 1) {  // accumulator fully read: hand the TMEM buffer back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(smem_u32(&bars->t_empty[tb]));
+                        }
 #pragma unroll
-                        for (int g = 0; g < 128; g += 16) {
-                            const int j0 = col_tile + g;
+                        for (int g = 0; g < 64; g += 16) {
+                            const int j0 = col_tile + hh * 64 + g;
                             int mx = v[g];
 #pragma unroll
                             for (int e = 1; e < 16; ++e) mx = max(mx, v[g + e]);
@@ -418,6 +419,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             }
                         }
                         __syncwarp();  // reconverge before the next .aligned tcgen05.ld
+                        }
                         if (kFused && __any_sync(0xFFFFFFFFu, qn >= kLaneQueue - 1)) drain();
                     }
                 }
