@@ -55,12 +55,16 @@ chol_diag(double *__restrict__ S, int ld, int k0, int kb, double *__restrict__ l
             double a[SB];
 #pragma unroll
             for (int c = 0; c < SB; ++c) a[c] = A[b + rl][b + c];
+            double inv_mine = 1.0;  // 1 / L[rl][rl]
 #pragma unroll
             for (int j = 0; j < SB; ++j) {
                 double d = __shfl_sync(0xFFFFFFFFu, a[j], j);
                 if (!(d > 0.0) || !isfinite(d)) bad = true, d = 1.0;
-                const double ljj = sqrt(d);
-                a[j] = rl == j ? ljj : a[j] / ljj;  // L[r][j] for r >= j
+                // the 64 pivots are a serial chain: rsqrt + multiplies instead of the much
+                // longer software sqrt and divide sequences
+                const double inv = rsqrt(d);
+                if (rl == j) inv_mine = inv;
+                a[j] = rl == j ? d * inv : a[j] * inv;  // L[r][j] for r >= j
 #pragma unroll
                 for (int c = j + 1; c < SB; ++c) {
                     const double lcj = __shfl_sync(0xFFFFFFFFu, a[j], c);
@@ -74,7 +78,7 @@ chol_diag(double *__restrict__ S, int ld, int k0, int kb, double *__restrict__ l
                 double v = rl == r ? 1.0 : 0.0;
 #pragma unroll
                 for (int p = 0; p < r; ++p) v = fma(-__shfl_sync(0xFFFFFFFFu, a[p], r), x[p], v);
-                x[r] = v / __shfl_sync(0xFFFFFFFFu, a[r], r);
+                x[r] = v * __shfl_sync(0xFFFFFFFFu, inv_mine, r);
             }
             if (lane < SB) {
 #pragma unroll

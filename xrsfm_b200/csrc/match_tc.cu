@@ -404,12 +404,23 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             if (kFused) {
                                 // lane-divergent slow path (a few % of the lanes): descend by quarters
                                 // of the group, park the hits in the lane's own queue
-                                if (mx > vlow && i < pd.n1)
-                                    qn = fused_slow16(qn, q, st_rows, st_cols, vlow, i, j0, pd.n2,
-                                                      make_int4(v[g], v[g + 1], v[g + 2], v[g + 3]),
-                                                      make_int4(v[g + 4], v[g + 5], v[g + 6], v[g + 7]),
-                                                      make_int4(v[g + 8], v[g + 9], v[g + 10], v[g + 11]),
-                                                      make_int4(v[g + 12], v[g + 13], v[g + 14], v[g + 15]));
+                                // lane-divergent slow path, inline and branch-light: one compare per
+                                // accumulator, hits go to the lane's private queue (an ABI call here
+                                // costs more in register save/restore than the work itself)
+                                if (mx > vlow && i < pd.n1) {
+#pragma unroll
+                                    for (int e = 0; e < 16; ++e) {
+                                        if (v[g + e] > vlow && j0 + e < pd.n2) {
+                                            if (qn < kLaneQueue) {
+                                                q[qn * 32] = ((unsigned long long)(unsigned)v[g + e] << 26) |
+                                                             ((unsigned long long)(unsigned)i << 13) | (unsigned)(j0 + e);
+                                                ++qn;
+                                            } else {
+                                                apply((uint32_t)v[g + e], (uint32_t)i, (uint32_t)(j0 + e));
+                                            }
+                                        }
+                                    }
+                                }
                             } else if (mx > vlow && i < pd.n1) {
                                 global_slow16(rows, cols, sbase, vlow, i, j0, pd.n2,
                                               make_int4(v[g], v[g + 1], v[g + 2], v[g + 3]),
