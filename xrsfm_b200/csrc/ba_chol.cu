@@ -5,7 +5,7 @@
 // Replaces Ceres' SparseSchurComplementSolver factor+solve (selected by ba_solver.cc:74).
 // Right-looking, block size 64:
 //   chol_diag    one CTA: L_kk = chol(A_kk) and its inverse, both in shared memory
-//   chol_panel   L_ik = A_ik Linv_kk^T   — FP64 GEMM tiles (128 x 64 x 64)
+//   chol_panel   L_ik = A_ik Linv_kk^T   — FP64 GEMM tiles (64 x 64 x 64)
 //   chol_update  A_ij -= L_ik L_jk^T     — FP64 GEMM tiles (128 x 128 x 64 or 64 x 64 x 64),
 //                lower-triangular tile pairs inside the band; this is where the n^3/3 flops are
 //   chol_backsolve  one launch per block column, bottom-up
@@ -213,13 +213,13 @@ struct Tile {
 __global__ void __launch_bounds__(256)
 chol_panel(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int rhs_row,
            const double *__restrict__ linv) {
-    using T = Tile<128, 64>;
+    using T = Tile<64, 64>;  // 64-row tiles: twice the CTAs of a 128-row split, half the latency
     extern __shared__ __align__(16) double smem_d[];
     double *Xs = smem_d, *Ys = smem_d + NB * T::LDX;
-    int row0 = r0 + blockIdx.x * 128;
-    int nrows = min(128, r1 - row0);
+    int row0 = r0 + blockIdx.x * 64;
+    int nrows = min(64, r1 - row0);
     if (row0 >= r1) row0 = rhs_row, nrows = 1;  // extra CTA: the right-hand-side row alone
-    T::stage<128>(Xs, T::LDX, S + (size_t)row0 * ld + k0, (size_t)ld, nrows, kb);
+    T::stage<64>(Xs, T::LDX, S + (size_t)row0 * ld + k0, (size_t)ld, nrows, kb);
     T::stage<64>(Ys, T::LDY, linv, (size_t)NB, NB, NB);  // Ys[p][j] = Linv[j][p]
     __syncthreads();
     double acc[T::RM][T::RN] = {};
@@ -235,12 +235,53 @@ chol_panel(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int r
 }
 
 // ---- 3. trailing update: A_ij -= L_ik L_jk^T for tiles j <= i inside the band ----------------
+// Software-pipelined over the depth: the 64-deep product is cut into 4 chunks of 16; while
+// chunk c is multiplied out of one shared-memory buffer, chunk c+1 travels global -> registers
+// -> the other buffer, so the L2 latency of the operand fetch hides behind the FP64 FMAs.
+constexpr int KC = 16;  // depth of one pipeline chunk
+
+template <int TT>
+struct UpdateCfg {
+    static constexpr int LDT = TT + 1;
+    static constexpr int kPerThread = TT * KC / 2 / 256;  // double2 loads per operand and thread
+    static constexpr int kSmemBytes = 2 * 2 * KC * LDT * (int)sizeof(double);
+};
+
+template <int TT>
+__device__ __forceinline__ void upd_fetch(const double *__restrict__ src, size_t ld, int nrows, int kb, int pc,
+                                          double2 (&v)[UpdateCfg<TT>::kPerThread]) {
+#pragma unroll
+    for (int u = 0; u < UpdateCfg<TT>::kPerThread; ++u) {
+        const int idx = threadIdx.x + u * 256, row = idx >> 3, p = pc + (idx & 7) * 2;  // 8 double2 per row
+        v[u] = make_double2(0.0, 0.0);
+        if (row < nrows) {
+            const double *g = src + (size_t)row * ld + p;
+            if (p + 1 < kb)
+                v[u] = __ldg(reinterpret_cast<const double2 *>(g));
+            else if (p < kb)
+                v[u].x = __ldg(g);
+        }
+    }
+}
+
+template <int TT>
+__device__ __forceinline__ void upd_store(double *dst, const double2 (&v)[UpdateCfg<TT>::kPerThread]) {
+#pragma unroll
+    for (int u = 0; u < UpdateCfg<TT>::kPerThread; ++u) {
+        const int idx = threadIdx.x + u * 256, row = idx >> 3, p = (idx & 7) * 2;
+        dst[p * UpdateCfg<TT>::LDT + row] = v[u].x;
+        dst[(p + 1) * UpdateCfg<TT>::LDT + row] = v[u].y;
+    }
+}
+
 template <int TT>
 __global__ void __launch_bounds__(256)
 chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int rhs_row) {
-    using T = Tile<TT, TT>;
+    using C = UpdateCfg<TT>;
+    constexpr int RM = TT / 16;
     extern __shared__ __align__(16) double smem_d[];
-    double *Xs = smem_d, *Ys = smem_d + NB * T::LDX;
+    double *Xs = smem_d;                      // [2][KC][LDT]
+    double *Ys = smem_d + 2 * KC * C::LDT;    // [2][KC][LDT]
     const int ntile = (r1 - r0 + TT - 1) / TT;
     const int ti = blockIdx.y, tj = blockIdx.x;
     int row0, nrows;
@@ -252,48 +293,104 @@ chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int 
     }
     if (tj >= ntile) return;
     const int col0 = r0 + tj * TT, ncols = min(TT, r1 - col0);
-    T::template stage<TT>(Xs, T::LDX, S + (size_t)row0 * ld + k0, (size_t)ld, nrows, kb);
-    T::template stage<TT>(Ys, T::LDY, S + (size_t)col0 * ld + k0, (size_t)ld, ncols, kb);
-    __syncthreads();
-    double acc[T::RM][T::RN] = {};
-    T::mma(Xs, Ys, acc);
-    const bool diag_tile = (ti < ntile) && (ti == tj);
+    const double *xsrc = S + (size_t)row0 * ld + k0, *ysrc = S + (size_t)col0 * ld + k0;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+    double2 vx[C::kPerThread], vy[C::kPerThread];
+    upd_fetch<TT>(xsrc, (size_t)ld, nrows, kb, 0, vx);
+    upd_fetch<TT>(ysrc, (size_t)ld, ncols, kb, 0, vy);
+    upd_store<TT>(Xs, vx);
+    upd_store<TT>(Ys, vy);
+    __syncthreads();
+    double acc[RM][RM] = {};
+#pragma unroll 1
+    for (int c = 0; c < NB / KC; ++c) {
+        const int cur = c & 1;
+        if (c + 1 < NB / KC) {
+            upd_fetch<TT>(xsrc, (size_t)ld, nrows, kb, (c + 1) * KC, vx);
+            upd_fetch<TT>(ysrc, (size_t)ld, ncols, kb, (c + 1) * KC, vy);
+        }
+        const double *xb = Xs + cur * KC * C::LDT, *yb = Ys + cur * KC * C::LDT;
+#pragma unroll 4
+        for (int p = 0; p < KC; ++p) {
+            double a[RM], b[RM];
 #pragma unroll
-    for (int i = 0; i < T::RM; ++i)
+            for (int i = 0; i < RM; ++i) a[i] = xb[p * C::LDT + ty + 16 * i];
 #pragma unroll
-        for (int j = 0; j < T::RN; ++j) {
-            const int r = ty + 16 * i, c = tx + 16 * j;
-            if (r < nrows && c < ncols && (!diag_tile || c <= r))
-                S[(size_t)(row0 + r) * ld + col0 + c] -= acc[i][j];
+            for (int j = 0; j < RM; ++j) b[j] = yb[p * C::LDT + tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+#pragma unroll
+                for (int j = 0; j < RM; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        if (c + 1 < NB / KC) {
+            upd_store<TT>(Xs + (cur ^ 1) * KC * C::LDT, vx);
+            upd_store<TT>(Ys + (cur ^ 1) * KC * C::LDT, vy);
+        }
+        __syncthreads();
+    }
+    const bool diag_tile = (ti < ntile) && (ti == tj);
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < RM; ++j) {
+            const int r = ty + 16 * i, cc = tx + 16 * j;
+            if (r < nrows && cc < ncols && (!diag_tile || cc <= r))
+                S[(size_t)(row0 + r) * ld + col0 + cc] -= acc[i][j];
         }
 }
 
-// ---- 4. backward substitution L^T x = y, one block column per launch ------------------------
-// Every CTA recomputes x_k = Linv_k^T y_k (64 x 64, trivial) and then removes x_k's
-// contribution from its slice of the earlier unknowns: y_j -= sum_r L[k0+r][j] x_k[r].
+// ---- 4. backward substitution L^T x = y, kBackGroup block columns per launch ------------------
+// Every CTA first solves the group's kBackGroup x 64 unknowns itself (bottom-up: remove the
+// already-solved blocks of the group from y_k, then x_k = Linv_k^T y_k; ~1k FMAs per thread,
+// redundant but far cheaper than a launch per block column), then removes the group's
+// contribution from its own 256-column slice of the earlier unknowns:
+//   y_j -= sum_g sum_r L[k0_g + r][j] x_g[r].
+constexpr int kBackGroup = 4;
+
 __global__ void __launch_bounds__(256)
-chol_backsolve(const double *__restrict__ S, int ld, int k0, int kb, int j0,
+chol_backsolve(const double *__restrict__ S, int ld, int n, int blk_hi, int nblk_group, int j0,
                const double *__restrict__ linv, double *__restrict__ y, double *__restrict__ x_out) {
-    __shared__ double xk[NB];
+    __shared__ double xk[kBackGroup][NB];
+    __shared__ double yt[NB];
     const int tid = threadIdx.x;
-    {
-        // x_k[c] = sum_{r >= c} Linv[r][c] y[k0 + r]; 4 lanes per column
-        const int c = tid >> 2, sub = tid & 3;
-        double v = 0.0;
-        if (c < kb)
-            for (int r = c + sub; r < kb; r += 4) v += linv[r * NB + c] * y[k0 + r];
-        v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
-        v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
-        if (sub == 0) xk[c] = c < kb ? v : 0.0;
+    for (int g = 0; g < nblk_group; ++g) {
+        const int k0 = (blk_hi - g) * NB, kb = min(NB, n - k0);
+        if (tid < NB) {
+            double v = 0.0;
+            if (tid < kb) {
+                v = y[k0 + tid];
+                for (int gp = 0; gp < g; ++gp) {
+                    const int kp0 = (blk_hi - gp) * NB, kpb = min(NB, n - kp0);
+                    for (int r = 0; r < kpb; ++r) v = fma(-S[(size_t)(kp0 + r) * ld + k0 + tid], xk[gp][r], v);
+                }
+            }
+            yt[tid] = v;
+        }
+        __syncthreads();
+        {
+            // x_k[c] = sum_{r >= c} Linv[r][c] yt[r]; 4 lanes per column
+            const double *li = linv + (size_t)(blk_hi - g) * NB * NB;
+            const int c = tid >> 2, sub = tid & 3;
+            double v = 0.0;
+            if (c < kb)
+                for (int r = c + sub; r < kb; r += 4) v = fma(li[r * NB + c], yt[r], v);
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+            if (sub == 0) xk[g][c] = c < kb ? v : 0.0;
+        }
+        __syncthreads();
+        if (blockIdx.x == 0 && tid < kb) x_out[k0 + tid] = xk[g][tid];
     }
-    __syncthreads();
-    if (blockIdx.x == 0 && tid < kb) x_out[k0 + tid] = xk[tid];
+    const int k_low = (blk_hi - nblk_group + 1) * NB;
     const int j = j0 + blockIdx.x * 256 + tid;
-    if (j < k0) {
+    if (j < k_low) {
         double acc = 0.0;
+        for (int g = 0; g < nblk_group; ++g) {
+            const int k0 = (blk_hi - g) * NB, kb = min(NB, n - k0);
 #pragma unroll 8
-        for (int r = 0; r < kb; ++r) acc = fma(S[(size_t)(k0 + r) * ld + j], xk[r], acc);
+            for (int r = 0; r < kb; ++r) acc = fma(S[(size_t)(k0 + r) * ld + j], xk[g][r], acc);
+        }
         y[j] -= acc;
     }
 }
@@ -313,27 +410,28 @@ int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, d
         chol_diag<<<1, 256, kDiagSmem, st>>>(S, ld, k0, kb, li, fail_flag);
         const int r0 = k0 + kb;
         const int r1 = min(n, r0 + bw);  // rows that can be non-zero in this block column
-        const int np = (r1 - r0 + 127) / 128;
-        chol_panel<<<np + 1, 256, Tile<128, 64>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n, li);
+        const int np = (r1 - r0 + 63) / 64;
+        chol_panel<<<np + 1, 256, Tile<64, 64>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n, li);
         // tile size: 128 while that still fills the machine, 64 for the tail
         const int nt128 = (r1 - r0 + 127) / 128;
         if (nt128 * (nt128 + 1) / 2 >= sms) {
             dim3 grid(nt128, nt128 + 1);
-            chol_update<128><<<grid, 256, Tile<128, 128>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n);
+            chol_update<128><<<grid, 256, UpdateCfg<128>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n);
         } else {
             const int nt64 = (r1 - r0 + 63) / 64;
             dim3 grid(nt64 > 0 ? nt64 : 1, nt64 + 1);
-            chol_update<64><<<grid, 256, Tile<64, 64>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n);
+            chol_update<64><<<grid, 256, UpdateCfg<64>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n);
         }
         nl += 3;
     }
     double *y = S + (size_t)n * ld;  // y = L^-1 rhs now sits in row n
-    for (int kblk = nblk - 1; kblk >= 0; --kblk) {
-        const int k0 = kblk * NB, kb = min(NB, n - k0);
-        const int j0 = max(0, k0 - bw - NB);
-        const int ncols = k0 - j0;
+    for (int hi = nblk - 1; hi >= 0; hi -= kBackGroup) {
+        const int ng = min(kBackGroup, hi + 1);
+        const int k_low = (hi - ng + 1) * NB;
+        const int j0 = max(0, k_low - bw - NB);
+        const int ncols = k_low - j0;
         const int grid = ncols > 0 ? (ncols + 255) / 256 : 1;
-        chol_backsolve<<<grid, 256, 0, st>>>(S, ld, k0, kb, j0, linv + (size_t)kblk * NB * NB, y, x_out);
+        chol_backsolve<<<grid, 256, 0, st>>>(S, ld, n, hi, ng, j0, linv, y, x_out);
         ++nl;
     }
     *count = nl;
@@ -356,11 +454,11 @@ int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, dou
     if (!attr_set) {
         XRB_CUDA(cudaFuncSetAttribute(chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
         XRB_CUDA(cudaFuncSetAttribute(chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Tile<128, 64>::kSmemBytes));
-        XRB_CUDA(cudaFuncSetAttribute(chol_update<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Tile<128, 128>::kSmemBytes));
-        XRB_CUDA(cudaFuncSetAttribute(chol_update<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Tile<64, 64>::kSmemBytes));
+        XRB_CUDA(cudaFuncSetAttribute(chol_update<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      UpdateCfg<128>::kSmemBytes));
+        XRB_CUDA(cudaFuncSetAttribute(chol_update<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      UpdateCfg<64>::kSmemBytes));
         attr_set = true;
     }
     // The launch sequence depends only on (n, ld, bw) and the buffers: replay it as a graph.

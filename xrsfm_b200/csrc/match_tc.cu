@@ -40,12 +40,13 @@ constexpr int kThreads = 32 * 10;
 constexpr int kFusedMax = 4096;
 constexpr int kLaneQueue = 4;  // candidates a lane can park before the warp drains
 template <bool kFused> struct Cfg {
-    static constexpr int kGroupN = kFused ? 768 : 1024;  // resident B descriptors per group
+    static constexpr int kGroupN = kFused ? 512 : 1024;  // resident B descriptors per group
     static constexpr int kBGroupBytes = kGroupN * kDim;
     static constexpr int kStateBytes = kFused ? 2 * kFusedMax * 8 : 0;
     static constexpr int kQueueBytes = kFused ? 8 * kLaneQueue * 32 * 8 : 0;
+    static constexpr int kScratchBytes = kFused ? 8 * 16 * 32 * 4 : 0;  // per lane: one group of 16 accumulators
     static constexpr int kSmemBytes = kBGroupBytes + kAStages * kATileBytes + kStateBytes + kQueueBytes +
-                                      1024 /*align*/ + 256 /*barriers*/;
+                                      kScratchBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------
@@ -238,7 +239,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     unsigned long long *st_rows = reinterpret_cast<unsigned long long *>(after);  // [kFusedMax]
     unsigned long long *st_cols = st_rows + (kFused ? kFusedMax : 0);             // [kFusedMax]
     unsigned long long *queues = st_cols + (kFused ? kFusedMax : 0);              // [8][64]
-    Bars *bars = reinterpret_cast<Bars *>(after + C::kStateBytes + C::kQueueBytes);
+    int *scratch_all = reinterpret_cast<int *>(after + C::kStateBytes + C::kQueueBytes);        // [8][16][32]
+    Bars *bars = reinterpret_cast<Bars *>(after + C::kStateBytes + C::kQueueBytes + C::kScratchBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -333,6 +335,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int vlow = *vlow_ptr;
         // per-lane private candidate queues: q[slot][lane]; no coordination needed to append
         unsigned long long *q = queues + ew * (kLaneQueue * 32) + lane;
+        int *scratch = scratch_all + ew * (16 * 32) + lane;  // [e][lane]: conflict-free
         int qn = 0;  // this lane's fill
         uint32_t t_it = 0;
         if (kFused) {
@@ -404,19 +407,24 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             if (kFused) {
                                 // lane-divergent slow path (a few % of the lanes): descend by quarters
                                 // of the group, park the hits in the lane's own queue
-                                // lane-divergent slow path, inline and branch-light: one compare per
-                                // accumulator, hits go to the lane's private queue (an ABI call here
-                                // costs more in register save/restore than the work itself)
+                                // lane-divergent slow path with a small code footprint: the lane dumps the
+                                // group's 16 accumulators to its private scratch column (static register
+                                // indices end here) and scans them in a ROLLED loop; hits are parked in the
+                                // lane's private queue.  (Unrolled compares or an ABI call per group cost
+                                // more in instruction-cache misses / register save-restore than the work.)
                                 if (mx > vlow && i < pd.n1) {
 #pragma unroll
+                                    for (int e = 0; e < 16; ++e) scratch[e * 32] = v[g + e];
+#pragma unroll 1
                                     for (int e = 0; e < 16; ++e) {
-                                        if (v[g + e] > vlow && j0 + e < pd.n2) {
+                                        const int val = scratch[e * 32];
+                                        if (val > vlow && j0 + e < pd.n2) {
                                             if (qn < kLaneQueue) {
-                                                q[qn * 32] = ((unsigned long long)(unsigned)v[g + e] << 26) |
+                                                q[qn * 32] = ((unsigned long long)(unsigned)val << 26) |
                                                              ((unsigned long long)(unsigned)i << 13) | (unsigned)(j0 + e);
                                                 ++qn;
                                             } else {
-                                                apply((uint32_t)v[g + e], (uint32_t)i, (uint32_t)(j0 + e));
+                                                apply((uint32_t)val, (uint32_t)i, (uint32_t)(j0 + e));
                                             }
                                         }
                                     }
