@@ -15,6 +15,7 @@
 
 #include <map>
 #include <tuple>
+#include <vector>
 
 #include "ba_kernels.cuh"
 
@@ -276,14 +277,14 @@ __device__ __forceinline__ void upd_store(double *dst, const double2 (&v)[Update
 
 template <int TT>
 __global__ void __launch_bounds__(256)
-chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int rhs_row) {
+chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int rhs_row, int tj_lo) {
     using C = UpdateCfg<TT>;
     constexpr int RM = TT / 16;
     extern __shared__ __align__(16) double smem_d[];
     double *Xs = smem_d;                      // [2][KC][LDT]
     double *Ys = smem_d + 2 * KC * C::LDT;    // [2][KC][LDT]
     const int ntile = (r1 - r0 + TT - 1) / TT;
-    const int ti = blockIdx.y, tj = blockIdx.x;
+    const int ti = blockIdx.y, tj = blockIdx.x + tj_lo;  // tile-column range [tj_lo, tj_lo + gridDim.x)
     int row0, nrows;
     if (ti < ntile) {
         if (tj > ti) return;
@@ -329,15 +330,27 @@ chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int 
         }
         __syncthreads();
     }
+    // C -= acc: a whole row of the register block is loaded before anything is stored, so the
+    // RM loads of a row are in flight together (a load/subtract/store chain per element
+    // exposes one L2 round trip per element: that was 60 % of this kernel's stall samples).
     const bool diag_tile = (ti < ntile) && (ti == tj);
 #pragma unroll
-    for (int i = 0; i < RM; ++i)
+    for (int i = 0; i < RM; ++i) {
+        const int r = ty + 16 * i;
+        double cv[RM];
 #pragma unroll
         for (int j = 0; j < RM; ++j) {
-            const int r = ty + 16 * i, cc = tx + 16 * j;
-            if (r < nrows && cc < ncols && (!diag_tile || cc <= r))
-                S[(size_t)(row0 + r) * ld + col0 + cc] -= acc[i][j];
+            const int cc = tx + 16 * j;
+            const bool ok = r < nrows && cc < ncols && (!diag_tile || cc <= r);
+            cv[j] = ok ? __ldcg(S + (size_t)(row0 + r) * ld + col0 + cc) : 0.0;
         }
+#pragma unroll
+        for (int j = 0; j < RM; ++j) {
+            const int cc = tx + 16 * j;
+            if (r < nrows && cc < ncols && (!diag_tile || cc <= r))
+                S[(size_t)(row0 + r) * ld + col0 + cc] = cv[j] - acc[i][j];
+        }
+    }
 }
 
 // ---- 4. backward substitution L^T x = y, kBackGroup block columns per launch ------------------
@@ -362,7 +375,15 @@ chol_backsolve(const double *__restrict__ S, int ld, int n, int blk_hi, int nblk
                 v = y[k0 + tid];
                 for (int gp = 0; gp < g; ++gp) {
                     const int kp0 = (blk_hi - gp) * NB, kpb = min(NB, n - kp0);
-                    for (int r = 0; r < kpb; ++r) v = fma(-S[(size_t)(kp0 + r) * ld + k0 + tid], xk[gp][r], v);
+                    double part[4] = {0.0, 0.0, 0.0, 0.0};  // independent chains: loads overlap
+#pragma unroll 4
+                    for (int r = 0; r + 3 < kpb; r += 4) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            part[u] = fma(__ldg(S + (size_t)(kp0 + r + u) * ld + k0 + tid), xk[gp][r + u], part[u]);
+                    }
+                    for (int r = kpb & ~3; r < kpb; ++r) part[0] = fma(__ldg(S + (size_t)(kp0 + r) * ld + k0 + tid), xk[gp][r], part[0]);
+                    v -= (part[0] + part[1]) + (part[2] + part[3]);
                 }
             }
             yt[tid] = v;
@@ -385,25 +406,54 @@ chol_backsolve(const double *__restrict__ S, int ld, int n, int blk_hi, int nblk
     const int k_low = (blk_hi - nblk_group + 1) * NB;
     const int j = j0 + blockIdx.x * 256 + tid;
     if (j < k_low) {
-        double acc = 0.0;
+        double part[4] = {0.0, 0.0, 0.0, 0.0};
         for (int g = 0; g < nblk_group; ++g) {
             const int k0 = (blk_hi - g) * NB, kb = min(NB, n - k0);
-#pragma unroll 8
-            for (int r = 0; r < kb; ++r) acc = fma(S[(size_t)(k0 + r) * ld + j], xk[g][r], acc);
+#pragma unroll 4
+            for (int r = 0; r + 3 < kb; r += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) part[u] = fma(__ldg(S + (size_t)(k0 + r + u) * ld + j), xk[g][r + u], part[u]);
+            }
+            for (int r = kb & ~3; r < kb; ++r) part[0] = fma(__ldg(S + (size_t)(k0 + r) * ld + j), xk[g][r], part[0]);
         }
-        y[j] -= acc;
+        y[j] -= (part[0] + part[1]) + (part[2] + part[3]);
     }
 }
 
 namespace {
+
+// Side stream + events for the look-ahead: the bulk of the trailing update of step k runs on
+// `side` while the main stream already factors the next diagonal block and forms the next
+// panel, which only need the FIRST tile column of that update.
+cudaStream_t g_side = nullptr;
+std::vector<cudaEvent_t> g_events;
+cudaEvent_t get_event(size_t i) {
+    while (g_events.size() <= i) {
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        g_events.push_back(e);
+    }
+    return g_events[i];
+}
+
+template <int TT>
+void launch_update(double *S, int ld, int k0, int kb, int r0, int r1, int n, int tj_lo, int tj_hi, cudaStream_t st) {
+    const int nt = (r1 - r0 + TT - 1) / TT;
+    if (tj_hi <= tj_lo) return;
+    dim3 grid(tj_hi - tj_lo, nt + 1);
+    chol_update<TT><<<grid, 256, UpdateCfg<TT>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n, tj_lo);
+}
 
 int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, double *fail_flag,
                 cudaStream_t st, int64_t *count) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!g_side) cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking);
     const int nblk = (n + NB - 1) / NB;
     int64_t nl = 0;
+    size_t ev = 0;
+    cudaEvent_t bulk_done = nullptr;  // completion of the previous step's bulk update
     for (int kblk = 0; kblk < nblk; ++kblk) {
         const int k0 = kblk * NB, kb = min(NB, n - k0);
         double *li = linv + (size_t)kblk * NB * NB;
@@ -412,18 +462,33 @@ int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, d
         const int r1 = min(n, r0 + bw);  // rows that can be non-zero in this block column
         const int np = (r1 - r0 + 63) / 64;
         chol_panel<<<np + 1, 256, Tile<64, 64>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n, li);
+        nl += 2;
+        cudaEvent_t panel_done = get_event(ev++);
+        cudaEventRecord(panel_done, st);
+        // first tile column on the main stream (after the previous bulk, whose tiles it touches)
+        if (bulk_done) cudaStreamWaitEvent(st, bulk_done, 0);
         // tile size: 128 while that still fills the machine, 64 for the tail
         const int nt128 = (r1 - r0 + 127) / 128;
-        if (nt128 * (nt128 + 1) / 2 >= sms) {
-            dim3 grid(nt128, nt128 + 1);
-            chol_update<128><<<grid, 256, UpdateCfg<128>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n);
-        } else {
-            const int nt64 = (r1 - r0 + 63) / 64;
-            dim3 grid(nt64 > 0 ? nt64 : 1, nt64 + 1);
-            chol_update<64><<<grid, 256, UpdateCfg<64>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n);
+        const bool big = nt128 * (nt128 + 1) / 2 >= sms;
+        const int nt = big ? nt128 : (r1 - r0 + 63) / 64;
+        if (big)
+            launch_update<128>(S, ld, k0, kb, r0, r1, n, 0, nt > 0 ? 1 : 0, st);
+        else
+            launch_update<64>(S, ld, k0, kb, r0, r1, n, 0, nt > 0 ? 1 : 0, st);
+        ++nl;
+        bulk_done = nullptr;
+        if (nt > 1) {
+            cudaStreamWaitEvent(g_side, panel_done, 0);
+            if (big)
+                launch_update<128>(S, ld, k0, kb, r0, r1, n, 1, nt, g_side);
+            else
+                launch_update<64>(S, ld, k0, kb, r0, r1, n, 1, nt, g_side);
+            ++nl;
+            bulk_done = get_event(ev++);
+            cudaEventRecord(bulk_done, g_side);
         }
-        nl += 3;
     }
+    if (bulk_done) cudaStreamWaitEvent(st, bulk_done, 0);
     double *y = S + (size_t)n * ld;  // y = L^-1 rhs now sits in row n
     for (int hi = nblk - 1; hi >= 0; hi -= kBackGroup) {
         const int ng = min(kBackGroup, hi + 1);

@@ -166,27 +166,18 @@ __device__ __forceinline__ void top2_update(unsigned long long *addr, uint32_t v
     } while (old != assumed);
 }
 
-// Out-of-line slow path of the fused epilogue (keeps the hot loop small enough for the
-// instruction cache): one lane found a group of 16 accumulators whose maximum exceeds v_low.
-// Hits are parked in the lane's private queue q[slot * 32]; a full queue applies directly.
-__device__ __noinline__ int fused_slow16(int qn, unsigned long long *q, unsigned long long *st_rows,
-                                         unsigned long long *st_cols, int vlow, int i, int j0, int n2, int4 a,
-                                         int4 b, int4 c, int4 d) {
-    const int v[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        if (v[e] > vlow && j0 + e < n2) {
-            if (qn < kLaneQueue) {
-                q[qn * 32] = ((unsigned long long)(unsigned)v[e] << 26) | ((unsigned long long)(unsigned)i << 13) |
-                             (unsigned)(j0 + e);
-                ++qn;
-            } else {
-                top2_update(st_rows + i, (uint32_t)v[e], 8191u - rank13_row((uint32_t)(j0 + e)));
-                top2_update(st_cols + j0 + e, (uint32_t)v[e], 8191u - (uint32_t)i);
-            }
-        }
+// Apply the candidates parked in one lane's private queue to the pair's top-2 state.  Kept out
+// of line on purpose: it is the only place with the 64-bit shared-memory CAS loops, it runs
+// rarely (a lane's queue fills up, or the warp drains after a tile), and the epilogue's hot
+// loop must stay small.
+__device__ __noinline__ void lane_flush(const unsigned long long *q, int qn, unsigned long long *st_rows,
+                                        unsigned long long *st_cols) {
+    for (int k = 0; k < qn; ++k) {
+        const unsigned long long e = q[k * 32];
+        const uint32_t v = (uint32_t)(e >> 26), i = (uint32_t)(e >> 13) & 0x1FFFu, j = (uint32_t)e & 0x1FFFu;
+        top2_update(st_rows + i, v, 8191u - rank13_row(j));
+        top2_update(st_cols + j, v, 8191u - i);
     }
-    return qn;
 }
 
 // Same for the global-state flavour: lock-free pushes into the per-row / per-column state.
@@ -342,28 +333,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             for (int z = et; z < 2 * kFusedMax; z += 256) st_rows[z] = 0ull;
             epi_bar();
         }
-        auto apply = [&](uint32_t val, uint32_t ii, uint32_t jj) {
-            top2_update(st_rows + ii, val, 8191u - rank13_row(jj));
-            top2_update(st_cols + jj, val, 8191u - ii);
-        };
         auto drain = [&]() {
-            for (int k = 0; k < kLaneQueue; ++k)
-                if (k < qn) {
-                    const unsigned long long e = q[k * 32];
-                    apply((uint32_t)(e >> 26), (uint32_t)(e >> 13) & 0x1FFFu, (uint32_t)e & 0x1FFFu);
-                }
+            lane_flush(q, qn, st_rows, st_cols);
             qn = 0;
             __syncwarp();
-        };
-        // a candidate found by this lane: park it, or (queue full: dense/adversarial input) apply now
-        auto park = [&](int val, int ii, int jj) {
-            if (qn < kLaneQueue) {
-                q[qn * 32] = ((unsigned long long)(unsigned)val << 26) | ((unsigned long long)(unsigned)ii << 13) |
-                             (unsigned)jj;
-                ++qn;
-            } else {
-                apply((uint32_t)val, (uint32_t)ii, (uint32_t)jj);
-            }
         };
         for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
             const PairDesc pd = pairs[p];
@@ -419,13 +392,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                     for (int e = 0; e < 16; ++e) {
                                         const int val = scratch[e * 32];
                                         if (val > vlow && j0 + e < pd.n2) {
-                                            if (qn < kLaneQueue) {
-                                                q[qn * 32] = ((unsigned long long)(unsigned)val << 26) |
-                                                             ((unsigned long long)(unsigned)i << 13) | (unsigned)(j0 + e);
-                                                ++qn;
-                                            } else {
-                                                apply((uint32_t)val, (uint32_t)i, (uint32_t)(j0 + e));
+                                            if (qn == kLaneQueue) {  // rare: this lane's queue is full
+                                                lane_flush(q, qn, st_rows, st_cols);
+                                                qn = 0;
                                             }
+                                            q[qn * 32] = ((unsigned long long)(unsigned)val << 26) |
+                                                         ((unsigned long long)(unsigned)i << 13) | (unsigned)(j0 + e);
+                                            ++qn;
                                         }
                                     }
                                 }
