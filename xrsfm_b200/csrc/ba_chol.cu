@@ -354,70 +354,81 @@ chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int 
 }
 
 // ---- 4. backward substitution L^T x = y, kBackGroup block columns per launch ------------------
-// Every CTA first solves the group's kBackGroup x 64 unknowns itself (bottom-up: remove the
-// already-solved blocks of the group from y_k, then x_k = Linv_k^T y_k; ~1k FMAs per thread,
-// redundant but far cheaper than a launch per block column), then removes the group's
-// contribution from its own 256-column slice of the earlier unknowns:
-//   y_j -= sum_g sum_r L[k0_g + r][j] x_g[r].
+// Thread layout (c, q): column c of a 64-column chunk, quarter q = one 64-row block of the
+// group; every dot product over 64 rows runs as 16 independent chains so 16 loads are in
+// flight per thread (the row stride makes each load a separate L2 sector stream).
+//   phase 1 (every CTA, redundantly, ~16 K FMAs): solve the group's kBackGroup x 64 unknowns
+//            bottom-up: y_k -= sum_{earlier blocks of the group} L_pk^T x_p ; x_k = Linv_k^T y_k
+//   phase 2: remove the group's contribution from this CTA's 64 earlier unknowns:
+//            y_j -= sum_g sum_r L[k0_g + r][j] x_g[r]
 constexpr int kBackGroup = 4;
+
+__device__ __forceinline__ double dot64_col(const double *__restrict__ base, size_t ld, int nrow,
+                                            const double *__restrict__ x) {
+    // sum_{r < nrow} base[r * ld] * x[r], 16 independent chains
+    double part[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) part[u] = 0.0;
+#pragma unroll
+    for (int r0 = 0; r0 < NB; r0 += 16) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = (r0 + u < nrow) ? __ldcg(base + (size_t)(r0 + u) * ld) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) part[u] = fma(v[u], x[r0 + u], part[u]);
+    }
+#pragma unroll
+    for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+        for (int u = 0; u < w; ++u) part[u] += part[u + w];
+    return part[0];
+}
 
 __global__ void __launch_bounds__(256)
 chol_backsolve(const double *__restrict__ S, int ld, int n, int blk_hi, int nblk_group, int j0,
                const double *__restrict__ linv, double *__restrict__ y, double *__restrict__ x_out) {
     __shared__ double xk[kBackGroup][NB];
+    __shared__ double red[4][NB];
     __shared__ double yt[NB];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, c = tid & 63, q = tid >> 6;
     for (int g = 0; g < nblk_group; ++g) {
         const int k0 = (blk_hi - g) * NB, kb = min(NB, n - k0);
-        if (tid < NB) {
-            double v = 0.0;
-            if (tid < kb) {
-                v = y[k0 + tid];
-                for (int gp = 0; gp < g; ++gp) {
-                    const int kp0 = (blk_hi - gp) * NB, kpb = min(NB, n - kp0);
-                    double part[4] = {0.0, 0.0, 0.0, 0.0};  // independent chains: loads overlap
-#pragma unroll 4
-                    for (int r = 0; r + 3 < kpb; r += 4) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            part[u] = fma(__ldg(S + (size_t)(kp0 + r + u) * ld + k0 + tid), xk[gp][r + u], part[u]);
-                    }
-                    for (int r = kpb & ~3; r < kpb; ++r) part[0] = fma(__ldg(S + (size_t)(kp0 + r) * ld + k0 + tid), xk[gp][r], part[0]);
-                    v -= (part[0] + part[1]) + (part[2] + part[3]);
-                }
-            }
-            yt[tid] = v;
+        // correction from the blocks of the group already solved: quarter q handles block gp = q
+        double corr = 0.0;
+        if (q < g && c < kb) {
+            const int kp0 = (blk_hi - q) * NB, kpb = min(NB, n - kp0);
+            corr = dot64_col(S + (size_t)kp0 * ld + k0 + c, (size_t)ld, kpb, xk[q]);
         }
+        red[q][c] = corr;
+        __syncthreads();
+        if (tid < NB) yt[tid] = tid < kb ? y[k0 + tid] - (red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid]) : 0.0;
         __syncthreads();
         {
-            // x_k[c] = sum_{r >= c} Linv[r][c] yt[r]; 4 lanes per column
+            // x_k[c] = sum_{r >= c} Linv[r][c] yt[r]; quarter q takes rows r = q, q+4, ...
             const double *li = linv + (size_t)(blk_hi - g) * NB * NB;
-            const int c = tid >> 2, sub = tid & 3;
             double v = 0.0;
             if (c < kb)
-                for (int r = c + sub; r < kb; r += 4) v = fma(li[r * NB + c], yt[r], v);
-            v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
-            v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
-            if (sub == 0) xk[g][c] = c < kb ? v : 0.0;
+                for (int r = c + q; r < kb; r += 4) v = fma(__ldg(li + r * NB + c), yt[r], v);
+            red[q][c] = v;
         }
         __syncthreads();
-        if (blockIdx.x == 0 && tid < kb) x_out[k0 + tid] = xk[g][tid];
+        if (tid < NB) {
+            const double v = tid < kb ? red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid] : 0.0;
+            xk[g][tid] = v;
+            if (blockIdx.x == 0 && tid < kb) x_out[k0 + tid] = v;
+        }
+        __syncthreads();
     }
     const int k_low = (blk_hi - nblk_group + 1) * NB;
-    const int j = j0 + blockIdx.x * 256 + tid;
-    if (j < k_low) {
-        double part[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int g = 0; g < nblk_group; ++g) {
-            const int k0 = (blk_hi - g) * NB, kb = min(NB, n - k0);
-#pragma unroll 4
-            for (int r = 0; r + 3 < kb; r += 4) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) part[u] = fma(__ldg(S + (size_t)(k0 + r + u) * ld + j), xk[g][r + u], part[u]);
-            }
-            for (int r = kb & ~3; r < kb; ++r) part[0] = fma(__ldg(S + (size_t)(k0 + r) * ld + j), xk[g][r], part[0]);
-        }
-        y[j] -= (part[0] + part[1]) + (part[2] + part[3]);
+    const int j = j0 + blockIdx.x * NB + c;
+    double part = 0.0;
+    if (j < k_low && q < nblk_group) {
+        const int k0 = (blk_hi - q) * NB, kb = min(NB, n - k0);
+        part = dot64_col(S + (size_t)k0 * ld + j, (size_t)ld, kb, xk[q]);
     }
+    red[q][c] = part;
+    __syncthreads();
+    if (tid < NB && j < k_low) y[j] -= red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
 }
 
 namespace {
@@ -495,7 +506,7 @@ int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, d
         const int k_low = (hi - ng + 1) * NB;
         const int j0 = max(0, k_low - bw - NB);
         const int ncols = k_low - j0;
-        const int grid = ncols > 0 ? (ncols + 255) / 256 : 1;
+        const int grid = ncols > 0 ? (ncols + NB - 1) / NB : 1;
         chol_backsolve<<<grid, 256, 0, st>>>(S, ld, n, hi, ng, j0, linv, y, x_out);
         ++nl;
     }
