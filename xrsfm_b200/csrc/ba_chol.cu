@@ -34,20 +34,10 @@ constexpr int NB = 64;  // block-column width == GEMM depth
 constexpr int SB = 16;
 constexpr int kDiagSmem = (2 * NB * (NB + 1) + NB * (SB + 1)) * (int)sizeof(double);
 
-__global__ void __launch_bounds__(256)
-chol_diag(double *__restrict__ S, int ld, int k0, int kb, double *__restrict__ linv_out,
-          double *__restrict__ fail) {
-    extern __shared__ __align__(16) double smem_d[];
-    double(*A)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d);                      // L when done
-    double(*X)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d + NB * (NB + 1));      // L^-1
-    double(*T)[SB + 1] = reinterpret_cast<double(*)[SB + 1]>(smem_d + 2 * NB * (NB + 1));  // scratch
+// In-place factorisation of the 64 x 64 block held in shared memory A (lower part, rows >= kb
+// made identity by the caller); on return A holds L and X holds L^-1.  256 threads.
+__device__ void diag_factor(double (*A)[NB + 1], double (*X)[NB + 1], double (*T)[SB + 1], double *__restrict__ fail) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int r = idx >> 6, c = idx & 63;
-        A[r][c] = (r < kb && c <= r) ? S[(size_t)(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
-        X[r][c] = 0.0;
-    }
-    __syncthreads();
     bool bad = false;
     for (int b = 0; b < NB; b += SB) {
         if (warp == 0) {
@@ -119,7 +109,7 @@ chol_diag(double *__restrict__ S, int ld, int k0, int kb, double *__restrict__ l
             __syncthreads();
         }
     }
-    if (bad && lane == 0) *fail = 1.0;
+    if (bad && tid == 0) *fail = 1.0;
     // ---- off-diagonal 16-blocks of X = L^-1, by block distance d: X_ij = -X_ii * sum_k L_ik X_kj
     for (int d = 1; d < NB / SB; ++d) {
         const int nblk = NB / SB - d;  // blocks (i, j = i - d), i = d .. 3
@@ -142,11 +132,33 @@ chol_diag(double *__restrict__ S, int ld, int k0, int kb, double *__restrict__ l
         }
         __syncthreads();
     }
-    for (int idx = tid; idx < NB * NB; idx += 256) {
+}
+
+// write L (lower, real rows) back into S and the inverse into its slot
+__device__ void diag_store(double (*A)[NB + 1], double (*X)[NB + 1], double *__restrict__ S, int ld, int k0, int kb,
+                           double *__restrict__ linv_out) {
+    for (int idx = threadIdx.x; idx < NB * NB; idx += 256) {
         const int r = idx >> 6, c = idx & 63;
         if (r < kb && c <= r) S[(size_t)(k0 + r) * ld + k0 + c] = A[r][c];
         linv_out[idx] = (r < kb && c < kb) ? X[r][c] : 0.0;
     }
+}
+
+__global__ void __launch_bounds__(256)
+chol_diag(double *__restrict__ S, int ld, int k0, int kb, double *__restrict__ linv_out,
+          double *__restrict__ fail) {
+    extern __shared__ __align__(16) double smem_d[];
+    double(*A)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d);                      // L when done
+    double(*X)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d + NB * (NB + 1));      // L^-1
+    double(*T)[SB + 1] = reinterpret_cast<double(*)[SB + 1]>(smem_d + 2 * NB * (NB + 1));  // scratch
+    for (int idx = threadIdx.x; idx < NB * NB; idx += 256) {
+        const int r = idx >> 6, c = idx & 63;
+        A[r][c] = (r < kb && c <= r) ? S[(size_t)(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
+        X[r][c] = 0.0;
+    }
+    __syncthreads();
+    diag_factor(A, X, T, fail);
+    diag_store(A, X, S, ld, k0, kb, linv_out);
 }
 
 // ---- FP64 GEMM tile: acc[i][j] = sum_p X[row(ty,i)][p] * Y[col(tx,j)][p], p < 64 -------------
@@ -277,7 +289,11 @@ __device__ __forceinline__ void upd_store(double *dst, const double2 (&v)[Update
 
 template <int TT>
 __global__ void __launch_bounds__(256)
-chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int rhs_row, int tj_lo) {
+chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int rhs_row, int tj_lo,
+            double *__restrict__ fuse_linv, double *__restrict__ fail) {
+    // fuse_linv != nullptr (TT == 64 only): the CTA of tile (0, 0) goes on to factor the block it
+    // has just updated — the next diagonal block — and writes its inverse to fuse_linv, which
+    // takes the stand-alone chol_diag launch off the critical path.
     using C = UpdateCfg<TT>;
     constexpr int RM = TT / 16;
     extern __shared__ __align__(16) double smem_d[];
@@ -334,6 +350,8 @@ chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int 
     // RM loads of a row are in flight together (a load/subtract/store chain per element
     // exposes one L2 round trip per element: that was 60 % of this kernel's stall samples).
     const bool diag_tile = (ti < ntile) && (ti == tj);
+    const bool fuse = TT == 64 && fuse_linv != nullptr && ti == 0 && tj == 0;
+    double(*FA)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d);  // aliases the operand stage
 #pragma unroll
     for (int i = 0; i < RM; ++i) {
         const int r = ty + 16 * i;
@@ -347,9 +365,21 @@ chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int 
 #pragma unroll
         for (int j = 0; j < RM; ++j) {
             const int cc = tx + 16 * j;
-            if (r < nrows && cc < ncols && (!diag_tile || cc <= r))
+            const bool ok = r < nrows && cc < ncols && (!diag_tile || cc <= r);
+            if (fuse) {
+                if (TT == 64) FA[r][cc] = ok ? cv[j] - acc[i][j] : (r == cc ? 1.0 : 0.0);
+            } else if (ok) {
                 S[(size_t)(row0 + r) * ld + col0 + cc] = cv[j] - acc[i][j];
+            }
         }
+    }
+    if (TT == 64 && fuse) {  // block-uniform branch
+        double(*FX)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d + NB * (NB + 1));
+        double(*FT)[SB + 1] = reinterpret_cast<double(*)[SB + 1]>(smem_d + 2 * NB * (NB + 1));
+        for (int idx = threadIdx.x; idx < NB * NB; idx += 256) FX[idx >> 6][idx & 63] = 0.0;
+        __syncthreads();
+        diag_factor(FA, FX, FT, fail);
+        diag_store(FA, FX, S, ld, r0, nrows, fuse_linv);
     }
 }
 
@@ -448,11 +478,14 @@ cudaEvent_t get_event(size_t i) {
 }
 
 template <int TT>
-void launch_update(double *S, int ld, int k0, int kb, int r0, int r1, int n, int tj_lo, int tj_hi, cudaStream_t st) {
+void launch_update(double *S, int ld, int k0, int kb, int r0, int r1, int n, int tj_lo, int tj_hi,
+                   double *fuse_linv, double *fail, cudaStream_t st) {
     const int nt = (r1 - r0 + TT - 1) / TT;
     if (tj_hi <= tj_lo) return;
     dim3 grid(tj_hi - tj_lo, nt + 1);
-    chol_update<TT><<<grid, 256, UpdateCfg<TT>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n, tj_lo);
+    const int smem = fuse_linv ? (UpdateCfg<TT>::kSmemBytes > kDiagSmem ? UpdateCfg<TT>::kSmemBytes : kDiagSmem)
+                               : UpdateCfg<TT>::kSmemBytes;
+    chol_update<TT><<<grid, 256, smem, st>>>(S, ld, k0, kb, r0, r1, n, tj_lo, fuse_linv, fail);
 }
 
 int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, double *fail_flag,
@@ -465,35 +498,45 @@ int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, d
     int64_t nl = 0;
     size_t ev = 0;
     cudaEvent_t bulk_done = nullptr;  // completion of the previous step's bulk update
+    chol_diag<<<1, 256, kDiagSmem, st>>>(S, ld, 0, min(NB, n), linv, fail_flag);  // block 0 only
+    ++nl;
     for (int kblk = 0; kblk < nblk; ++kblk) {
         const int k0 = kblk * NB, kb = min(NB, n - k0);
         double *li = linv + (size_t)kblk * NB * NB;
-        chol_diag<<<1, 256, kDiagSmem, st>>>(S, ld, k0, kb, li, fail_flag);
         const int r0 = k0 + kb;
         const int r1 = min(n, r0 + bw);  // rows that can be non-zero in this block column
         const int np = (r1 - r0 + 63) / 64;
         chol_panel<<<np + 1, 256, Tile<64, 64>::kSmemBytes, st>>>(S, ld, k0, kb, r0, r1, n, li);
-        nl += 2;
+        ++nl;
         cudaEvent_t panel_done = get_event(ev++);
         cudaEventRecord(panel_done, st);
-        // first tile column on the main stream (after the previous bulk, whose tiles it touches)
+        // critical part on the main stream: the first 64 columns of the trailing matrix (the
+        // next block column), after the previous bulk whose tiles it touches; its (0, 0) CTA
+        // also factors the next diagonal block
         if (bulk_done) cudaStreamWaitEvent(st, bulk_done, 0);
-        // tile size: 128 while that still fills the machine, 64 for the tail
-        const int nt128 = (r1 - r0 + 127) / 128;
-        const bool big = nt128 * (nt128 + 1) / 2 >= sms;
-        const int nt = big ? nt128 : (r1 - r0 + 63) / 64;
-        if (big)
-            launch_update<128>(S, ld, k0, kb, r0, r1, n, 0, nt > 0 ? 1 : 0, st);
-        else
-            launch_update<64>(S, ld, k0, kb, r0, r1, n, 0, nt > 0 ? 1 : 0, st);
-        ++nl;
+        if (r1 > r0) {
+            // fusing needs the whole next diagonal block inside this update's row range (a band
+            // narrower than one block leaves rows the update never loads)
+            const int kb_next = min(NB, n - r0);
+            const bool fuse_ok = kblk + 1 < nblk && (r1 - r0) >= kb_next;
+            double *li_next = linv + (size_t)(kblk + 1) * NB * NB;
+            launch_update<64>(S, ld, k0, kb, r0, r1, n, 0, 1, fuse_ok ? li_next : nullptr, fail_flag, st);
+            ++nl;
+            if (!fuse_ok && kblk + 1 < nblk) {
+                chol_diag<<<1, 256, kDiagSmem, st>>>(S, ld, r0, kb_next, li_next, fail_flag);
+                ++nl;
+            }
+        }
+        // bulk on the side stream: everything from column r0 + 64 on
         bulk_done = nullptr;
-        if (nt > 1) {
+        const int b0 = r0 + NB;
+        if (r1 > b0) {
             cudaStreamWaitEvent(g_side, panel_done, 0);
-            if (big)
-                launch_update<128>(S, ld, k0, kb, r0, r1, n, 1, nt, g_side);
+            const int nt128 = (r1 - b0 + 127) / 128;
+            if (nt128 * (nt128 + 1) / 2 >= sms)
+                launch_update<128>(S, ld, k0, kb, b0, r1, n, 0, nt128, nullptr, fail_flag, g_side);
             else
-                launch_update<64>(S, ld, k0, kb, r0, r1, n, 1, nt, g_side);
+                launch_update<64>(S, ld, k0, kb, b0, r1, n, 0, (r1 - b0 + 63) / 64, nullptr, fail_flag, g_side);
             ++nl;
             bulk_done = get_event(ev++);
             cudaEventRecord(bulk_done, g_side);
@@ -534,7 +577,7 @@ int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, dou
         XRB_CUDA(cudaFuncSetAttribute(chol_update<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       UpdateCfg<128>::kSmemBytes));
         XRB_CUDA(cudaFuncSetAttribute(chol_update<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      UpdateCfg<64>::kSmemBytes));
+                                      UpdateCfg<64>::kSmemBytes > kDiagSmem ? UpdateCfg<64>::kSmemBytes : kDiagSmem));
         attr_set = true;
     }
     // The launch sequence depends only on (n, ld, bw) and the buffers: replay it as a graph.

@@ -171,6 +171,14 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// sum over the LPP lanes that share one point (LPP = 32: the warp, 16: a half warp)
+template <int LPP>
+__device__ __forceinline__ double group_sum(double v, unsigned gmask) {
+#pragma unroll
+    for (int d = LPP / 2; d > 0; d >>= 1) v += __shfl_xor_sync(gmask, v, d);
+    return v;
+}
+
 __device__ __forceinline__ void atomic_max_nonneg(double *addr, double v) {
     // non-negative doubles order like their bit patterns
     atomicMax(reinterpret_cast<unsigned long long *>(addr),
@@ -492,22 +500,27 @@ int ba_launch_schur(const BAProblemDev &P, const BAStateDev &x, const BAConsts &
 //                 rhs_c = sum Jc^T (r - JX h), S_cc -= sum Tt_i Tt_i^T, block-reduced.
 // The result is deterministic (fixed summation order) and S is written exactly once.
 // =====================================================================================
+template <int LPP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_lin(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L, double inv_radius, double *__restrict__ scalars) {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    // LPP lanes per point: a 32-lane warp serves 32 / LPP points at once (short tracks waste
+    // most of a full warp); `lane` below is the lane within the point's group
+    constexpr int kGroups = 32 / LPP;
+    const int lane = threadIdx.x & (LPP - 1);
+    const unsigned gmask = LPP == 32 ? 0xFFFFFFFFu : (((1u << LPP) - 1u) << (((threadIdx.x & 31) / LPP) * LPP));
+    const int warp = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kGroups + ((threadIdx.x & 31) / LPP);
+    const int nwarps = ((gridDim.x * blockDim.x) >> 5) * kGroups;
     double gmax = 0.0;
     for (int p = warp; p < P.n_pts_local; p += nwarps) {
         const int k0 = P.pt_ptr[p], kn = P.pt_ptr[p + 1] - k0;
         if (kn == 0) continue;
         const bool pvar = P.pt_var[p] != 0;
-        const int nchunks = (kn + kChunk - 1) / kChunk;
+        const int nchunks = (kn + LPP - 1) / LPP;
         double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
         LinObs lo;
         lo.active = false;
         for (int ch = 0; ch < nchunks; ++ch) {
-            const int i = ch * kChunk + lane;
+            const int i = ch * LPP + lane;
             lo.active = false;
             if (i < kn) lin_obs(P, x, k, L, k0 + i, p, pvar, lo);
             if (lo.active) {
@@ -521,9 +534,9 @@ k_lin(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L, double inv_radius, d
             }
         }
 #pragma unroll
-        for (int j = 0; j < 6; ++j) V[j] = warp_sum(V[j]);
+        for (int j = 0; j < 6; ++j) V[j] = group_sum<LPP>(V[j], gmask);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) g[j] = warp_sum(g[j]);
+        for (int j = 0; j < 3; ++j) g[j] = group_sum<LPP>(g[j], gmask);
         // (V + D^2) = Lc Lc^T (3x3 Cholesky); Tt = W Lc^-T so that Tt_i Tt_j^T = W_i (V+D^2)^-1 W_j^T
         double l00 = 1, l10 = 0, l11 = 1, l20 = 0, l21 = 0, l22 = 1;
         if (pvar) {
@@ -560,7 +573,7 @@ k_lin(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L, double inv_radius, d
             L.h[3 * (size_t)p] = L.h[3 * (size_t)p + 1] = L.h[3 * (size_t)p + 2] = 0.0;
         }
         for (int ch = 0; ch < nchunks; ++ch) {
-            const int i = ch * kChunk + lane;
+            const int i = ch * LPP + lane;
             if (nchunks > 1) {
                 lo.active = false;
                 if (i < kn) lin_obs(P, x, k, L, k0 + i, p, pvar, lo);
@@ -594,7 +607,11 @@ k_lin(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L, double inv_radius, d
 int ba_launch_lin(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k, const BALinSys &L,
                   double inv_radius, double *scalars, cudaStream_t st) {
     if (P.n_pts_local > 0) {
-        k_lin<<<point_grid(P.n_pts_local), kWarpsPerCta * 32, 0, st>>>(P, x, k, L, inv_radius, scalars);
+        // short tracks (mean <= 16 observations): two points per warp
+        if ((long long)P.n_obs_local <= 16LL * P.n_pts_local)
+            k_lin<16><<<point_grid((P.n_pts_local + 1) / 2), kWarpsPerCta * 32, 0, st>>>(P, x, k, L, inv_radius, scalars);
+        else
+            k_lin<32><<<point_grid(P.n_pts_local), kWarpsPerCta * 32, 0, st>>>(P, x, k, L, inv_radius, scalars);
         XRB_LAUNCHED();
     }
     XRB_CUDA(cudaGetLastError());
@@ -804,23 +821,28 @@ int ba_launch_cam_diag(const BAProblemDev &P, const BAStateDev &x, const BALinSy
 // 4. Back-substitution y_p = V^-1 (g_p - sum W_i^T y_c), candidate point, model cost change
 //    -(J s)^T (r + J s / 2) and step / state norms, one warp per point.
 // =====================================================================================
+template <int LPP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_backsub(BAProblemDev P, BAStateDev x, BAStateDev cand, BAConsts k, BALinSys L,
           const double *__restrict__ yc, double *__restrict__ step_p, double *__restrict__ scalars) {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    // LPP lanes per point: a 32-lane warp serves 32 / LPP points at once (short tracks waste
+    // most of a full warp); `lane` below is the lane within the point's group
+    constexpr int kGroups = 32 / LPP;
+    const int lane = threadIdx.x & (LPP - 1);
+    const unsigned gmask = LPP == 32 ? 0xFFFFFFFFu : (((1u << LPP) - 1u) << (((threadIdx.x & 31) / LPP) * LPP));
+    const int warp = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kGroups + ((threadIdx.x & 31) / LPP);
+    const int nwarps = ((gridDim.x * blockDim.x) >> 5) * kGroups;
     double model = 0.0, sn2 = 0.0, xn2 = 0.0;
     for (int p = warp; p < P.n_pts_local; p += nwarps) {
         const int k0 = P.pt_ptr[p], kn = P.pt_ptr[p + 1] - k0;
         const bool pvar = P.pt_var[p] != 0;
-        const int nchunks = (kn + kChunk - 1) / kChunk;
+        const int nchunks = (kn + LPP - 1) / LPP;
         double acc0 = 0, acc1 = 0, acc2 = 0;
         LinObs lo;
         lo.active = false;
         double jy0 = 0, jy1 = 0;
         for (int ch = 0; ch < nchunks; ++ch) {
-            const int i = ch * kChunk + lane;
+            const int i = ch * LPP + lane;
             lo.active = false;
             if (i < kn) lin_obs(P, x, k, L, k0 + i, p, pvar, lo);
             jy0 = jy1 = 0.0;
@@ -836,7 +858,7 @@ k_backsub(BAProblemDev P, BAStateDev x, BAStateDev cand, BAConsts k, BALinSys L,
                 acc2 += lo.JX[2] * jy0 + lo.JX[5] * jy1;
             }
         }
-        acc0 = warp_sum(acc0), acc1 = warp_sum(acc1), acc2 = warp_sum(acc2);
+        acc0 = group_sum<LPP>(acc0, gmask), acc1 = group_sum<LPP>(acc1, gmask), acc2 = group_sum<LPP>(acc2, gmask);
         double y0 = 0, y1 = 0, y2 = 0;
         if (pvar) {
             const double *Vi = L.Vinv + 6 * (size_t)p;
@@ -864,7 +886,7 @@ k_backsub(BAProblemDev P, BAStateDev x, BAStateDev cand, BAConsts k, BALinSys L,
         }
         // model residual m = J s = -(Jc yc + JX yp); contribution -(m . (r + m / 2))
         for (int ch = 0; ch < nchunks; ++ch) {
-            const int i = ch * kChunk + lane;
+            const int i = ch * LPP + lane;
             if (nchunks > 1) {
                 lo.active = false;
                 if (i < kn) lin_obs(P, x, k, L, k0 + i, p, pvar, lo);
@@ -885,7 +907,7 @@ k_backsub(BAProblemDev P, BAStateDev x, BAStateDev cand, BAConsts k, BALinSys L,
             }
         }
     }
-    model = warp_sum(model);
+    model = group_sum<LPP>(model, gmask);
     if (lane == 0) {
         atomicAdd(&scalars[SC_MODEL_CHANGE], model);
         atomicAdd(&scalars[SC_STEP_NORM2], sn2);
@@ -897,7 +919,10 @@ int ba_launch_backsub(const BAProblemDev &P, const BAStateDev &x, const BAStateD
                       const BAConsts &k, const BALinSys &L, const double *yc, double *step_p,
                       double *scalars, cudaStream_t st) {
     if (P.n_pts_local > 0) {
-        k_backsub<<<point_grid(P.n_pts_local), kWarpsPerCta * 32, 0, st>>>(P, x, cand, k, L, yc, step_p, scalars);
+        if ((long long)P.n_obs_local <= 16LL * P.n_pts_local)
+            k_backsub<16><<<point_grid((P.n_pts_local + 1) / 2), kWarpsPerCta * 32, 0, st>>>(P, x, cand, k, L, yc, step_p, scalars);
+        else
+            k_backsub<32><<<point_grid(P.n_pts_local), kWarpsPerCta * 32, 0, st>>>(P, x, cand, k, L, yc, step_p, scalars);
         XRB_LAUNCHED();
     }
     XRB_CUDA(cudaGetLastError());
