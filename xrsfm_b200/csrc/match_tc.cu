@@ -388,21 +388,34 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                 if (mx > vlow && i < pd.n1) {
                                     unsigned hits = 0;
 #pragma unroll
-                                    for (int e = 0; e < 16; ++e) {
-                                        hits |= (unsigned)(v[g + e] > vlow) << e;  // branch-free, static registers
-                                        scratch[e * 32] = v[g + e];
-                                    }
-                                    while (hits) {  // one or two iterations: only the hits are re-read
+                                    for (int e = 0; e < 16; ++e) hits |= (unsigned)(v[g + e] > vlow) << e;  // static regs
+                                    if ((hits & (hits - 1)) == 0) {
+                                        // the usual case, a single hit: it is the group's maximum, no re-read
                                         const int e = __ffs(hits) - 1;
-                                        hits &= hits - 1;
                                         if (j0 + e < pd.n2) {
-                                            if (qn == kLaneQueue) {  // rare: this lane's queue is full
+                                            if (qn == kLaneQueue) {
                                                 lane_flush(q, qn, st_rows, st_cols);
                                                 qn = 0;
                                             }
-                                            q[qn * 32] = ((unsigned long long)(unsigned)scratch[e * 32] << 26) |
+                                            q[qn * 32] = ((unsigned long long)(unsigned)mx << 26) |
                                                          ((unsigned long long)(unsigned)i << 13) | (unsigned)(j0 + e);
                                             ++qn;
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int e = 0; e < 16; ++e) scratch[e * 32] = v[g + e];
+                                        while (hits) {
+                                            const int e = __ffs(hits) - 1;
+                                            hits &= hits - 1;
+                                            if (j0 + e < pd.n2) {
+                                                if (qn == kLaneQueue) {  // rare: this lane's queue is full
+                                                    lane_flush(q, qn, st_rows, st_cols);
+                                                    qn = 0;
+                                                }
+                                                q[qn * 32] = ((unsigned long long)(unsigned)scratch[e * 32] << 26) |
+                                                             ((unsigned long long)(unsigned)i << 13) | (unsigned)(j0 + e);
+                                                ++qn;
+                                            }
                                         }
                                     }
                                 }
