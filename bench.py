@@ -99,7 +99,11 @@ def host_cores():
 
 
 def dist_env():
-    return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if os.environ.get("XRB_BENCH_ONE_GPU"):  # dry run of the N > 1 control flow on a 1-GPU box (gloo)
+        local_rank = 0
+    return rank, world, local_rank
 
 
 class _CudaPtr:
@@ -126,9 +130,11 @@ def make_c2(scale=1.0):
         except Exception:
             pass
     sc = synth.make_scene("C2", scale)
-    try:
-        np.savez(cache, dims=np.array([sc.n_cams, sc.n_pts, sc.n_obs, sc.n_intr]), **{k: sc[k] for k in keys})
-    except OSError:
+    try:  # atomic publish: several ranks may build the scene at the same time
+        tmp = f"{cache}.{os.getpid()}.tmp.npz"
+        np.savez(tmp, dims=np.array([sc.n_cams, sc.n_pts, sc.n_obs, sc.n_intr]), **{k: sc[k] for k in keys})
+        os.replace(tmp, cache)
+    except Exception:
         pass
     return sc
 
@@ -260,7 +266,12 @@ def run_ba(args, rank, world, local_rank):
         "clocks": clk,
         "roofline": {"kernel": "k_gather (Schur complement: per-block gather of the observation records)",
                      "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": ach / peak, "traffic": None, "algorithmic_bytes_per_launch": gather_bytes,
+                     "frac": ach / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one k_gather launch on this
+                     # very scene, from the ncu --set full capture summarised in profiles/
+                     "traffic": 1.355e9 if args.scale == 1.0 else None,
+                     "traffic_source": "profiles/r01c_gather_and_update_summary.md",
+                     "algorithmic_bytes_per_launch": gather_bytes,
                      "ms_per_launch": kern_ms["k_gather"],
                      "note": "HBM-bound kernel of the iteration; the largest share of the time is the FP64 "
                              "Cholesky (see roofline_fp64), which is bound by the FP64 FMA pipe, not HBM"},
@@ -481,7 +492,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl")
+        dist.init_process_group(os.environ.get("XRB_BENCH_BACKEND", "nccl"))
     out = None
     if args.path in ("both", "ba"):
         out = run_ba(args, rank, world, local_rank)

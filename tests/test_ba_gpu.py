@@ -227,3 +227,54 @@ def test_bad_arguments_are_rejected(solver):
     bad2.intr_model = np.array([7], dtype=np.int32)
     with pytest.raises(Exception):
         solver.solve_scene(bad2, **ol.GBA_FAST)
+
+
+def test_degenerate_structure(solver):
+    """Cameras without observations stay out of the problem, a point seen once is rescued by the
+    LM diagonal, an all-constant problem converges immediately."""
+    sc = synth.make_sphere_scene(8, 120, 4, 95, behind_frac=0.0)
+    keep = sc.obs_cam != 5                      # camera 5 loses all its observations
+    keep &= ~((sc.obs_pt == 7) & (np.cumsum(sc.obs_pt == 7) > 1))  # point 7 keeps one observation
+    sc2 = sc.copy_state()
+    for k in ("obs_cam", "obs_pt"):
+        sc2[k] = np.ascontiguousarray(sc[k][keep])
+    sc2["obs_uv"] = np.ascontiguousarray(sc.obs_uv[keep])
+    sc2["n_obs"] = int(keep.sum())
+    got, ref, s_got, s_ref = _run_both(solver, sc2, **ol.GBA_FAST)
+    _compare_logs(s_got, s_ref, rel=1e-6)
+    _compare_states(got, ref)
+    np.testing.assert_array_equal(got.cam_q[5], sc.cam_q[5])  # untouched
+    assert s_got.num_effective_parameters_reduced == 6 * 7 - 6 + 3 * 120
+    # everything constant
+    sc3 = synth.make_sphere_scene(4, 30, 3, 96, behind_frac=0.0)
+    sc3.cam_q_fixed[:] = 1
+    sc3.cam_t_fixed[:] = 1
+    sc3.pt_fixed[:] = 1
+    s3 = solver.solve_scene(sc3.copy_state(), **ol.GBA_FAST)
+    s3r = ol.ba_solve(sc3.copy_state(), ol.ba_options(**ol.GBA_FAST))
+    assert s3.termination_type == s3r.termination_type == 0
+    assert s3.num_lm_iterations == s3r.num_lm_iterations == 0
+    assert s3.final_cost == pytest.approx(s3r.final_cost, rel=1e-12)
+    # no observations at all
+    sc4 = sc3.copy_state()
+    for k in ("obs_cam", "obs_pt"):
+        sc4[k] = np.zeros(0, dtype=np.int32)
+    sc4["obs_uv"] = np.zeros((0, 2))
+    sc4["n_obs"] = 0
+    s4 = solver.solve_scene(sc4, **ol.GBA_FAST)
+    assert s4.termination_type == 0 and s4.num_residuals_reduced == 0
+
+
+def test_generation1_schur_kernel_still_agrees(monkeypatch):
+    """XRB_BA_SCHUR=1 selects the atomics-based k_schur: same results as the gather pipeline."""
+    monkeypatch.setenv("XRB_BA_SCHUR", "1")
+    s1 = ba.BASolver()
+    sc = synth.make_scene("C1")
+    a = sc.copy_state()
+    r1 = s1.solve_scene(a, **ol.GBA_ACCURATE)
+    monkeypatch.delenv("XRB_BA_SCHUR")
+    b = sc.copy_state()
+    r2 = ba.BASolver().solve_scene(b, **ol.GBA_ACCURATE)
+    assert r1.num_lm_iterations == r2.num_lm_iterations
+    assert r1.final_cost == pytest.approx(r2.final_cost, rel=1e-9)
+    assert np.abs(a.pts - b.pts).max() < 1e-8

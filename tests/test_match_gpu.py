@@ -184,3 +184,20 @@ def test_full_size_properties(matcher):
         assert len(found & planted) >= 0.98 * len(planted)
         assert len(found - planted) <= 0.01 * len(planted) + 2
     matcher.set_variant(0)
+
+
+def test_images_above_the_fused_limit_fall_back_to_the_global_state_path():
+    """> 4096 descriptors per image: generation 3 hands over to generation 2 (same MMA pipeline,
+    top-2 state in global memory); the reference allows up to 8192 features per image
+    (feature_extraction.cc:24) and Allocate(16384)."""
+    m = matching.SiftMatchGPU()
+    assert matching.CreateSiftGPUMatcher(m)  # max_sift 16384 like the reference
+    imgs, _ = synth.make_images(2, 5000, seed=51)
+    d1, d2 = imgs[0], imgs[1][:4500]
+    exp = ol.match_pair(d1, d2)
+    got = matching.SiftMatch(d1, d2, m)
+    np.testing.assert_array_equal(got, exp)
+    m.upload_images([d1, d2, imgs[1][:100]])
+    off, mm = m.match_pairs(np.array([[0, 1], [2, 0]], dtype=np.int32))
+    np.testing.assert_array_equal(mm[off[0]: off[1]], exp)
+    np.testing.assert_array_equal(mm[off[1]: off[2]], ol.match_pair(imgs[1][:100], d1))
