@@ -386,9 +386,15 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                 // lane's private queue.  (Unrolled compares or an ABI call per group cost
                                 // more in instruction-cache misses / register save-restore than the work.)
                                 if (mx > vlow && i < pd.n1) {
-                                    unsigned hits = 0;
+                                    // hit mask as a shallow tree (16 independent compares, 3 levels of
+                                    // 3-input ORs) rather than a 16-long dependent chain
+                                    unsigned hb[16];
 #pragma unroll
-                                    for (int e = 0; e < 16; ++e) hits |= (unsigned)(v[g + e] > vlow) << e;  // static regs
+                                    for (int e = 0; e < 16; ++e) hb[e] = v[g + e] > vlow ? (1u << e) : 0u;
+                                    const unsigned h0 = hb[0] | hb[1] | hb[2], h1 = hb[3] | hb[4] | hb[5];
+                                    const unsigned h2 = hb[6] | hb[7] | hb[8], h3 = hb[9] | hb[10] | hb[11];
+                                    const unsigned h4 = hb[12] | hb[13] | hb[14];
+                                    unsigned hits = (h0 | h1 | h2) | (h3 | h4 | hb[15]);
                                     if ((hits & (hits - 1)) == 0) {
                                         // the usual case, a single hit: it is the group's maximum, no re-read
                                         const int e = __ffs(hits) - 1;
