@@ -324,7 +324,8 @@ def gen_descriptors_torch(n_images, n_feat, seed, device):
     return out
 
 
-def run_match(args, rank, world, local_rank, n_images=256, n_feat=4096):
+def run_match(args, rank, world, local_rank, n_feat=4096):
+    n_images = args.match_images
     import torch
     from xrsfm_b200 import _lib, matching, synth
     torch.cuda.set_device(local_rank)
@@ -334,6 +335,7 @@ def run_match(args, rank, world, local_rank, n_images=256, n_feat=4096):
     pairs_all = synth.sequential_pairs(n_images, window=19, n_retrieval=5, seed=2)
     pairs = pairs_all[rank::world].copy()  # pair-sharded, no collective
     m = matching.SiftMatchGPU(n_feat)
+    m.SetLanguage(matching.SiftMatchGPU.SIFTMATCH_CUDA_DEVICE0 + local_rank)  # feature_processing.cc:66-71
     assert m.VerifyContextGL() == 1, _lib.last_error()
     offs = np.arange(n_images + 1, dtype=np.int64) * n_feat
     _lib.check(lib.xrb_match_attach_device(m._h, n_images, offs.ctypes.data, block.data_ptr()), "attach")
@@ -364,6 +366,7 @@ def run_match(args, rank, world, local_rank, n_images=256, n_feat=4096):
     host_block.copy_(block.view(-1, 128))
     hb = host_block.numpy()
     m2 = matching.SiftMatchGPU(n_feat)
+    m2.SetLanguage(matching.SiftMatchGPU.SIFTMATCH_CUDA_DEVICE0 + local_rank)
     assert m2.VerifyContextGL() == 1
     t0 = time.perf_counter()
     m2.upload_packed(offs, hb)
@@ -389,7 +392,7 @@ def run_match(args, rank, world, local_rank, n_images=256, n_feat=4096):
         "ms_per_pass": ms, "pairs_per_pass": total_pairs, "n_gpus": world, "dtype": "u8",
         "config": {"workload": f"C3-shaped: {n_images} images x {n_feat} x 128-D uint8, "
                                f"{pairs_all.shape[0]} pairs (window 19 + 5 pseudo-retrieval), distmax 0.7, "
-                               "ratio 0.8, mutual best; descriptor set (134 MB at 256 images) > L2",
+                               f"ratio 0.8, mutual best; descriptor set ({n_images * n_feat * 128 / 1e6:.0f} MB) > L2",
                    "variant": int(lib.xrb_match_set_variant(m._h, 0))},
         "e2e": {"value": total_pairs / e2e_s, "unit": "pairs/s",
                 "h2d_bytes_per_step": int(hb.nbytes + pairs.nbytes), "d2h_bytes_per_step": int(mm.nbytes + off.nbytes),
@@ -478,6 +481,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--path", default="both", choices=["both", "ba", "match"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink C2 (tests only; 1.0 = the named config)")
+    ap.add_argument("--match-images", type=int, default=2000, help="images of the matching leg (C3 = 2000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world, local_rank = dist_env()

@@ -168,6 +168,37 @@ def test_batched_pairs_equal_per_pair_oracle(matcher):
         matcher.match_pairs(pairs, capacity=3)
 
 
+def test_pipelined_chunks_keep_pair_order_and_offsets(matcher):
+    """xrb_match_pairs drains chunk c on a copy stream while chunk c + 1 is scored (chunks of 512
+    pairs): > 3 chunks of ragged small images, every pair against the oracle, offsets monotone."""
+    n_img = 40
+    rng = np.random.default_rng(11)
+    imgs, _ = synth.make_images(n_img, 160, seed=77)
+    imgs = [im[: int(rng.integers(60, 161))] for im in imgs]
+    a, b = np.meshgrid(np.arange(n_img), np.arange(n_img), indexing="ij")
+    pairs = np.stack([a.ravel(), b.ravel()], axis=1).astype(np.int32)  # 1600 pairs incl. (i, i)
+    matcher.set_variant(0)
+    matcher.upload_images(imgs)
+    off, mm = matcher.match_pairs(pairs)
+    assert off[0] == 0 and np.all(np.diff(off) >= 0) and off[-1] == mm.shape[0]
+    for p in rng.choice(pairs.shape[0], 200, replace=False).tolist() + [0, 511, 512, 1023, 1024, 1599]:
+        i, j = pairs[p]
+        np.testing.assert_array_equal(mm[off[p]: off[p + 1]], ol.match_pair(imgs[i], imgs[j]))
+    # a second call reuses the double buffers
+    off2, mm2 = matcher.match_pairs(pairs[:700])
+    np.testing.assert_array_equal(off2, off[:701])
+    np.testing.assert_array_equal(mm2, mm[: off[700]])
+
+
+def test_device_pointers_must_be_device_memory():
+    m = matching.SiftMatchGPU(64)
+    assert m.VerifyContextGL() == 1
+    host = np.zeros((64, 128), dtype=np.uint8)
+    offs = np.array([0, 64], dtype=np.int64)
+    rc = _lib.lib().xrb_match_attach_device(m._h, 1, offs.ctypes.data, host.ctypes.data)
+    assert rc == -1 and "attach_device" in _lib.last_error()  # XRB_ERR_INVALID
+
+
 def test_full_size_properties(matcher):
     """4096 x 4096 (config C3 per-pair size): properties that need no oracle —
     symmetry under swapping the images, planted correspondences recovered, indices unique."""

@@ -15,7 +15,7 @@
 #include <numeric>
 #include <vector>
 
-#include "ba_kernels.cuh"
+#include "ba_structure.cuh"
 
 using namespace xrb;
 
@@ -43,13 +43,13 @@ struct xrb_ba_solver {
     int P_local = 0, O_local = 0, p_lo = 0;
     int nc = 0, ld = 0, bw = 0;
     int n_var_q = 0, n_var_t = 0, n_var_pts = 0, n_res_blocks = 0;
-    std::vector<int32_t> obs_orig_host;
 
     // device: problem
     DevBuf d_intr, d_intr_model, d_cam_intr, d_colq, d_colt, d_pt_ptr, d_obs_cam, d_obs_uv,
         d_pt_var, d_obs_orig;
     // generation-2 Schur structure (ba_struct.cu) and per-observation records
     DevBuf d_obs_pt, d_cam_ptr, d_cam_obs, d_inc, d_blk_ptr, d_blk_cams, d_Tt, d_h;
+    BAStructScratch W;  // ba_load.cu / ba_struct.cu working set, kept between loads
     int schur_gen = 2, n_blocks = 0;
     int64_t n_inc = 0;
     // device: states
@@ -142,11 +142,6 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
         return XRB_ERR_INVALID;
     }
     const int C = P->n_cams, NP = P->n_pts, NO = P->n_obs;
-    for (int o = 0; o < NO; ++o)
-        if (P->obs_cam[o] < 0 || P->obs_cam[o] >= C || P->obs_pt[o] < 0 || P->obs_pt[o] >= NP) {
-            set_error("ba_load: observation %d references camera %d / point %d out of range", o, P->obs_cam[o], P->obs_pt[o]);
-            return XRB_ERR_INVALID;
-        }
     for (int c = 0; c < C; ++c)
         if (P->cam_intr[c] < 0 || P->cam_intr[c] >= P->n_intr) {
             set_error("ba_load: camera %d references intrinsics %d out of range", c, P->cam_intr[c]);
@@ -158,117 +153,46 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
             return XRB_ERR_INVALID;
         }
     s->C = C, s->P_total = NP, s->O_total = NO, s->n_intr = P->n_intr;
-    lt.lap("validate");
+    s->loaded = false;
 
-    // ---- global structure: CSR by point (stable), variable blocks, reduced columns
-    std::vector<int> pt_ptr(NP + 1, 0), cam_obs(C, 0);
-    for (int o = 0; o < NO; ++o) pt_ptr[P->obs_pt[o] + 1]++, cam_obs[P->obs_cam[o]]++;
-    for (int p = 0; p < NP; ++p) pt_ptr[p + 1] += pt_ptr[p];
-    std::vector<int> pt_obs(NO);
-    {
-        std::vector<int> cursor(pt_ptr.begin(), pt_ptr.end() - 1);
-        for (int o = 0; o < NO; ++o) pt_obs[cursor[P->obs_pt[o]]++] = o;
-    }
-    std::vector<int32_t> colq(C, -1), colt(C, -1);
-    s->nc = 0, s->n_var_q = s->n_var_t = 0;
-    for (int c = 0; c < C; ++c) {
-        if (!cam_obs[c]) continue;  // not in the ceres::Problem at all
-        if (!(P->cam_q_fixed && P->cam_q_fixed[c])) colq[c] = s->nc, s->nc += 3, s->n_var_q++;
-        if (!(P->cam_t_fixed && P->cam_t_fixed[c])) colt[c] = s->nc, s->nc += 3, s->n_var_t++;
-    }
-    std::vector<uint8_t> pt_var(NP, 0);
-    s->n_var_pts = 0;
-    for (int p = 0; p < NP; ++p)
-        if (pt_ptr[p + 1] > pt_ptr[p] && !(P->pt_fixed && P->pt_fixed[p])) pt_var[p] = 1, s->n_var_pts++;
-    s->n_res_blocks = 0;
-    for (int o = 0; o < NO; ++o) {
-        const int c = P->obs_cam[o];
-        s->n_res_blocks += (colq[c] >= 0 || colt[c] >= 0 || pt_var[P->obs_pt[o]]) ? 1 : 0;
-    }
-    // half bandwidth of S in scalars
-    int bw = 0;
-    for (int p = 0; p < NP; ++p) {
-        if (!pt_var[p]) continue;
-        int lo = INT32_MAX, hi = -1;
-        for (int k = pt_ptr[p]; k < pt_ptr[p + 1]; ++k) {
-            const int c = P->obs_cam[pt_obs[k]];
-            if (colq[c] >= 0) lo = std::min(lo, colq[c]), hi = std::max(hi, colq[c] + 2);
-            if (colt[c] >= 0) lo = std::min(lo, colt[c]), hi = std::max(hi, colt[c] + 2);
-        }
-        if (hi >= 0) bw = std::max(bw, hi - lo);
-    }
-    s->bw = std::max(bw, 5);
-    lt.lap("csr + columns + bandwidth");
-
-    // ---- shard the points over ranks, balanced by the Schur work (xrb_ba_shard_range)
-    int p_lo = 0, p_hi = NP;
-    if (s->world > 1) {
-        std::vector<int32_t> kp(NP);
-        for (int p = 0; p < NP; ++p) kp[p] = pt_ptr[p + 1] - pt_ptr[p];
-        int32_t lo32 = 0, hi32 = NP;
-        xrb_ba_shard_range(NP, kp.data(), s->rank, s->world, &lo32, &hi32);
-        p_lo = lo32, p_hi = hi32;
-    }
-    s->p_lo = p_lo, s->P_local = p_hi - p_lo;
-    const int o_lo = pt_ptr[p_lo], o_hi = pt_ptr[p_hi];
-    s->O_local = o_hi - o_lo;
-    std::vector<int32_t> l_ptr(s->P_local + 1), l_cam(s->O_local), l_orig(s->O_local);
-    std::vector<double> l_uv(2 * (size_t)s->O_local);
-    for (int p = 0; p <= s->P_local; ++p) l_ptr[p] = pt_ptr[p_lo + p] - o_lo;
-    for (int k = 0; k < s->O_local; ++k) {
-        const int o = pt_obs[o_lo + k];
-        l_cam[k] = P->obs_cam[o], l_orig[k] = o;
-        l_uv[2 * (size_t)k] = P->obs_uv[2 * (size_t)o], l_uv[2 * (size_t)k + 1] = P->obs_uv[2 * (size_t)o + 1];
-    }
-    s->obs_orig_host = l_orig;
-
+    // ---- structure on the device (ba_load.cu): CSRs, variable flags, bandwidth, shard
     int rc;
+    BAStructBufs out{&s->d_colq, &s->d_colt, &s->d_pt_ptr, &s->d_obs_cam, &s->d_obs_uv, &s->d_pt_var,
+                     &s->d_obs_orig, &s->d_obs_pt, &s->d_cam_ptr, &s->d_cam_obs};
+    BAStructInfo info{};
+    if ((rc = ba_build_structure(P, s->rank, s->world, s->W, out, &info, st))) return rc;
+    s->nc = info.nc, s->n_var_q = info.n_var_q, s->n_var_t = info.n_var_t, s->n_var_pts = info.n_var_pts;
+    s->n_res_blocks = info.n_res_blocks, s->bw = info.bw;
+    s->p_lo = info.p_lo, s->P_local = info.P_local, s->O_local = info.O_local;
+    lt.lap("structure (device)");
+
     if ((rc = upload(s->d_intr, P->intr, 8 * (size_t)P->n_intr, st))) return rc;
     if ((rc = upload(s->d_intr_model, P->intr_model, (size_t)P->n_intr, st))) return rc;
     if ((rc = upload(s->d_cam_intr, P->cam_intr, (size_t)C, st))) return rc;
-    if ((rc = upload(s->d_colq, colq.data(), (size_t)C, st))) return rc;
-    if ((rc = upload(s->d_colt, colt.data(), (size_t)C, st))) return rc;
-    if ((rc = upload(s->d_pt_ptr, l_ptr.data(), l_ptr.size(), st))) return rc;
-    if ((rc = upload(s->d_obs_cam, l_cam.data(), l_cam.size(), st))) return rc;
-    if ((rc = upload(s->d_obs_orig, l_orig.data(), l_orig.size(), st))) return rc;
-    if ((rc = upload(s->d_obs_uv, l_uv.data(), l_uv.size(), st))) return rc;
-    if ((rc = upload(s->d_pt_var, pt_var.data() + p_lo, (size_t)s->P_local, st))) return rc;
-    for (int i = 0; i < 3; ++i) {
-        if ((rc = upload(s->d_q[i], P->cam_q, 4 * (size_t)C, st))) return rc;
-        if ((rc = upload(s->d_t[i], P->cam_t, 3 * (size_t)C, st))) return rc;
-        if ((rc = upload(s->d_X[i], P->pts + 3 * (size_t)p_lo, 3 * (size_t)s->P_local, st))) return rc;
+    if ((rc = upload(s->d_q[0], P->cam_q, 4 * (size_t)C, st))) return rc;
+    if ((rc = upload(s->d_t[0], P->cam_t, 3 * (size_t)C, st))) return rc;
+    if ((rc = upload(s->d_X[0], P->pts + 3 * (size_t)s->p_lo, 3 * (size_t)s->P_local, st))) return rc;
+    for (int i = 1; i < 3; ++i) {  // candidate slot and the copy xrb_ba_reset restores
+        if ((rc = s->d_q[i].reserve(std::max<size_t>(1, 4 * (size_t)C) * 8))) return rc;
+        if ((rc = s->d_t[i].reserve(std::max<size_t>(1, 3 * (size_t)C) * 8))) return rc;
+        if ((rc = s->d_X[i].reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
+        if (C) XRB_CUDA(cudaMemcpyAsync(s->d_q[i].p, s->d_q[0].p, 4 * (size_t)C * 8, cudaMemcpyDeviceToDevice, st));
+        if (C) XRB_CUDA(cudaMemcpyAsync(s->d_t[i].p, s->d_t[0].p, 3 * (size_t)C * 8, cudaMemcpyDeviceToDevice, st));
+        if (s->P_local)
+            XRB_CUDA(cudaMemcpyAsync(s->d_X[i].p, s->d_X[0].p, 3 * (size_t)s->P_local * 8, cudaMemcpyDeviceToDevice, st));
     }
     s->cur = 0;
-    lt.lap("shard + uploads");
-    // ---- generation-2 Schur structure: obs -> point, camera-major CSR, block incidence lists
+    lt.lap("state + intrinsics uploads");
+    // ---- generation-2 Schur structure: per-observation records, block incidence lists
     {
         const char *env = getenv("XRB_BA_SCHUR");
         s->schur_gen = (env && atoi(env) == 1) ? 1 : 2;
-        std::vector<int32_t> l_pt(s->O_local), c_ptr(C + 1, 0), c_obs(s->O_local);
-        for (int p = 0; p < s->P_local; ++p)
-            for (int k = l_ptr[p]; k < l_ptr[p + 1]; ++k) l_pt[k] = p;
-        for (int k = 0; k < s->O_local; ++k) c_ptr[l_cam[k] + 1]++;
-        for (int c = 0; c < C; ++c) c_ptr[c + 1] += c_ptr[c];
-        {
-            std::vector<int32_t> cursor(c_ptr.begin(), c_ptr.end() - 1);
-            for (int k = 0; k < s->O_local; ++k) c_obs[cursor[l_cam[k]]++] = k;
-        }
-        if ((rc = upload(s->d_obs_pt, l_pt.data(), l_pt.size(), st))) return rc;
-        if ((rc = upload(s->d_cam_ptr, c_ptr.data(), c_ptr.size(), st))) return rc;
-        if ((rc = upload(s->d_cam_obs, c_obs.data(), c_obs.size(), st))) return rc;
         s->n_blocks = 0, s->n_inc = 0;
         if (s->schur_gen == 2) {
-            std::vector<int64_t> pair_ptr(s->P_local + 1, 0);
-            for (int p = 0; p < s->P_local; ++p) {
-                const int64_t k = l_ptr[p + 1] - l_ptr[p];
-                pair_ptr[p + 1] = pair_ptr[p] + k * (k - 1) / 2;
-            }
             if ((rc = s->d_Tt.reserve(std::max<size_t>(1, 18 * (size_t)s->O_local) * 8))) return rc;
             if ((rc = s->d_h.reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
             BAProblemDev pd = s->prob();
-            pd.nc = s->nc;
-            lt.lap("cam-major csr + uploads");
-            if ((rc = ba_build_block_lists(pd, pair_ptr, s->d_inc, s->d_blk_ptr, s->d_blk_cams, &s->n_blocks, &s->n_inc, st)))
+            if ((rc = ba_build_block_lists(pd, s->W, s->d_inc, s->d_blk_ptr, s->d_blk_cams, &s->n_blocks, &s->n_inc, st)))
                 return rc;
             lt.lap("block lists (device)");
         }
@@ -650,6 +574,7 @@ void xrb_ba_destroy(xrb_ba_solver *s) {
                       &s->d_obs_pt, &s->d_cam_ptr, &s->d_cam_obs, &s->d_inc, &s->d_blk_ptr, &s->d_blk_cams,
                       &s->d_Tt, &s->d_h};
     for (DevBuf *b : bufs) b->release();
+    s->W.release();
     for (int i = 0; i < 3; ++i) s->d_q[i].release(), s->d_t[i].release(), s->d_X[i].release();
     if (s->h_scal) cudaFreeHost(s->h_scal);
     cudaStreamDestroy(s->own_stream);

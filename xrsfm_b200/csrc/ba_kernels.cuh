@@ -90,9 +90,6 @@ int ba_launch_lin(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
 int ba_launch_gather(const BAProblemDev &P, const BALinSys &L, cudaStream_t st);
 int ba_launch_cam_blocks(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
                          const BALinSys &L, cudaStream_t st);
-int ba_build_block_lists(const BAProblemDev &P, const std::vector<int64_t> &pair_ptr_host, DevBuf &d_inc,
-                         DevBuf &d_blk_ptr, DevBuf &d_blk_cams, int *n_blocks, int64_t *n_inc,
-                         cudaStream_t st);
 int ba_launch_cam_diag(const BAProblemDev &P, const BAStateDev &x, const BALinSys &L,
                        double inv_radius, double *scalars, cudaStream_t st);
 int ba_launch_backsub(const BAProblemDev &P, const BAStateDev &x, const BAStateDev &cand,

@@ -18,7 +18,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "ba_kernels.cuh"
+#include "ba_structure.cuh"
 
 namespace xrb {
 
@@ -69,65 +69,74 @@ __global__ void k_fill_blocks(int64_t n, const unsigned long long *__restrict__ 
     blk_ptr[b] = (int32_t)i;
 }
 
-int ba_build_block_lists(const BAProblemDev &P, const std::vector<int64_t> &pair_ptr_host, DevBuf &d_inc,
-                         DevBuf &d_blk_ptr, DevBuf &d_blk_cams, int *n_blocks, int64_t *n_inc,
-                         cudaStream_t st) {
-    const int64_t total = pair_ptr_host.empty() ? 0 : pair_ptr_host.back();
+// unordered observation pairs of each local point: k (k - 1) / 2, and a trailing 0 for the scan
+__global__ void k_pair_count(int n_pts, const int32_t *__restrict__ pt_ptr, int64_t *__restrict__ cnt) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > n_pts) return;
+    const int64_t k = p < n_pts ? pt_ptr[p + 1] - pt_ptr[p] : 0;
+    cnt[p] = k * (k - 1) / 2;
+}
+
+int ba_build_block_lists(const BAProblemDev &P, BAStructScratch &W, DevBuf &d_inc, DevBuf &d_blk_ptr,
+                         DevBuf &d_blk_cams, int *n_blocks, int64_t *n_inc, cudaStream_t st) {
     *n_blocks = 0, *n_inc = 0;
-    if (total == 0 || P.n_pts_local == 0) {
-        int rc = d_blk_ptr.reserve(16);
-        return rc;
+    int rc;
+    if ((rc = d_blk_ptr.reserve(16))) return rc;
+    if (P.n_pts_local == 0) return XRB_OK;
+    if ((rc = W.pair_ptr.reserve(((size_t)P.n_pts_local + 1) * 8))) return rc;
+    auto pol = thrust::cuda::par_nosync(W.pool).on(st);
+    int64_t total = 0;
+    k_pair_count<<<(P.n_pts_local + 1 + 255) / 256, 256, 0, st>>>(P.n_pts_local, P.pt_ptr, W.pair_ptr.as<int64_t>());
+    XRB_LAUNCHED();
+    try {
+        thrust::device_ptr<int64_t> c(W.pair_ptr.as<int64_t>());
+        thrust::exclusive_scan(pol, c, c + P.n_pts_local + 1, c);
+    } catch (const std::exception &e) {
+        set_error("ba: building the block lists failed: %s", e.what());
+        return XRB_ERR_CUDA;
     }
+    XRB_CUDA(cudaMemcpyAsync(&total, W.pair_ptr.as<int64_t>() + P.n_pts_local, 8, cudaMemcpyDeviceToHost, st));
+    XRB_CUDA(cudaStreamSynchronize(st));
+    if (total == 0) return XRB_OK;
     if (total >= (int64_t)INT32_MAX) {
         set_error("ba: %lld observation pairs exceed the 2^31 limit of the block lists", (long long)total);
         return XRB_ERR_INVALID;
     }
-    DevBuf d_pair_ptr, d_keys, d_head, d_scan;
-    int rc;
-    if ((rc = d_pair_ptr.reserve(pair_ptr_host.size() * 8))) return rc;
-    if ((rc = d_keys.reserve((size_t)total * 8))) return rc;
+    if ((rc = W.keys64.reserve((size_t)total * 8))) return rc;
     if ((rc = d_inc.reserve((size_t)total * 8))) return rc;
-    if ((rc = d_head.reserve((size_t)total * 4))) return rc;
-    if ((rc = d_scan.reserve((size_t)total * 4))) return rc;
-    XRB_CUDA(cudaMemcpyAsync(d_pair_ptr.p, pair_ptr_host.data(), pair_ptr_host.size() * 8, cudaMemcpyHostToDevice, st));
-    k_enum_pairs<<<(P.n_pts_local + 127) / 128, 128, 0, st>>>(P.n_pts_local, P.pt_ptr, d_pair_ptr.as<int64_t>(), P.obs_cam,
-                                                           P.pt_var, P.colq, P.colt, d_keys.as<unsigned long long>(),
-                                                           d_inc.as<int2>());
+    if ((rc = W.head.reserve((size_t)total * 4))) return rc;
+    if ((rc = W.scan.reserve((size_t)total * 4))) return rc;
+    unsigned long long *keys = W.keys64.as<unsigned long long>();
+    k_enum_pairs<<<(P.n_pts_local + 127) / 128, 128, 0, st>>>(P.n_pts_local, P.pt_ptr, W.pair_ptr.as<int64_t>(), P.obs_cam,
+                                                           P.pt_var, P.colq, P.colt, keys, d_inc.as<int2>());
     XRB_LAUNCHED();
     XRB_CUDA(cudaGetLastError());
+    int64_t valid = total;
     try {
-        auto pol = thrust::cuda::par.on(st);
-        thrust::device_ptr<unsigned long long> k(d_keys.as<unsigned long long>());
+        thrust::device_ptr<unsigned long long> k(keys);
         thrust::device_ptr<int2> v(d_inc.as<int2>());
         thrust::sort_by_key(pol, k, k + total, v);
-        k_mark_heads<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, d_keys.as<unsigned long long>(), d_head.as<int32_t>());
+        k_mark_heads<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, keys, W.head.as<int32_t>());
         XRB_LAUNCHED();
-        thrust::device_ptr<int32_t> h(d_head.as<int32_t>()), s(d_scan.as<int32_t>());
+        thrust::device_ptr<int32_t> h(W.head.as<int32_t>()), s(W.scan.as<int32_t>());
         thrust::inclusive_scan(pol, h, h + total, s);
+        // number of valid incidences = index of the first invalid key (they sort last)
+        valid = thrust::lower_bound(thrust::cuda::par(W.pool).on(st), k, k + total, ~0ull) - k;
     } catch (const std::exception &e) {
         set_error("ba: building the block lists failed: %s", e.what());
-        d_pair_ptr.release(), d_keys.release(), d_head.release(), d_scan.release();
         return XRB_ERR_CUDA;
     }
     int32_t nb = 0;
-    XRB_CUDA(cudaMemcpyAsync(&nb, d_scan.as<int32_t>() + (total - 1), 4, cudaMemcpyDeviceToHost, st));
+    XRB_CUDA(cudaMemcpyAsync(&nb, W.scan.as<int32_t>() + (total - 1), 4, cudaMemcpyDeviceToHost, st));
     XRB_CUDA(cudaStreamSynchronize(st));
     if ((rc = d_blk_ptr.reserve((size_t)(nb + 1) * 4))) return rc;
     if ((rc = d_blk_cams.reserve(std::max<size_t>(1, (size_t)nb) * 8))) return rc;
-    k_fill_blocks<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, d_keys.as<unsigned long long>(), d_scan.as<int32_t>(),
-                                                                    d_head.as<int32_t>(), d_blk_cams.as<int2>(),
-                                                                    d_blk_ptr.as<int32_t>());
+    k_fill_blocks<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, keys, W.scan.as<int32_t>(), W.head.as<int32_t>(),
+                                                                    d_blk_cams.as<int2>(), d_blk_ptr.as<int32_t>());
     XRB_LAUNCHED();
-    // number of valid incidences = index of the first invalid key (they sort last)
-    int64_t valid = total;
-    {
-        thrust::device_ptr<unsigned long long> k(d_keys.as<unsigned long long>());
-        valid = thrust::lower_bound(thrust::cuda::par.on(st), k, k + total, ~0ull) - k;
-    }
     const int32_t v32 = (int32_t)valid;
     XRB_CUDA(cudaMemcpyAsync(d_blk_ptr.as<int32_t>() + nb, &v32, 4, cudaMemcpyHostToDevice, st));
     XRB_CUDA(cudaStreamSynchronize(st));
-    d_pair_ptr.release(), d_keys.release(), d_head.release(), d_scan.release();
     *n_blocks = nb, *n_inc = valid;
     return XRB_OK;
 }

@@ -32,9 +32,37 @@ struct xrb_matcher {
     DevBuf pairdesc, counts, strided, packed, pack_offsets, vlow, pair_idx;
     DevBuf dist_tab;  // float(acos(double(min(v*2^-18,1)))) for v = 0..2^18 (generation 3)
     int strided_stride = 0;
+    // host-output pipeline of xrb_match_pairs: chunk c's match lists travel to the caller's
+    // buffer on copy_stream while chunk c+1 is being scored
+    DevBuf packed2, pack_offsets2;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_off[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    int64_t *h_off[2] = {nullptr, nullptr};
+    size_t h_off_cap = 0;
 };
 
 namespace {
+
+// A device pointer handed in by the caller must live on the matcher's GPU: the kernels would fault
+// on a pointer of another device (no peer mapping is set up), long after the call returned.
+int check_on_device(const xrb_matcher *m, const void *p, const char *what) {
+    if (!p) return XRB_OK;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("%s: not a CUDA pointer", what);
+        return XRB_ERR_INVALID;
+    }
+    if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) {
+        set_error("%s: expected device memory", what);
+        return XRB_ERR_INVALID;
+    }
+    if (a.type == cudaMemoryTypeDevice && a.device != m->device) {
+        set_error("%s lives on GPU %d but the matcher was created on GPU %d", what, a.device, m->device);
+        return XRB_ERR_INVALID;
+    }
+    return XRB_OK;
+}
 
 int ensure_scratch(xrb_matcher *m, int n_pairs_hint) {
     // Size the batch so the top-2 state stays below ~512 MiB.
@@ -142,6 +170,13 @@ void xrb_match_destroy(xrb_matcher *m) {
                       &m->counts, &m->strided, &m->packed, &m->pack_offsets, &m->vlow,
                       &m->pair_idx, &m->dist_tab};
     for (DevBuf *b : bufs) b->release();
+    m->packed2.release(), m->pack_offsets2.release();
+    for (int b = 0; b < 2; ++b) {
+        if (m->ev_off[b]) cudaEventDestroy(m->ev_off[b]);
+        if (m->ev_copied[b]) cudaEventDestroy(m->ev_copied[b]);
+        if (m->h_off[b]) cudaFreeHost(m->h_off[b]);
+    }
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -283,6 +318,7 @@ int xrb_match_attach_device(xrb_matcher *m, int n_images, const int64_t *row_off
         return XRB_ERR_INVALID;
     }
     XRB_CUDA(cudaSetDevice(m->device));
+    if (int rc = check_on_device(m, desc_block_device, "attach_device: descriptor block")) return rc;
     m->block = desc_block_device;
     return set_offsets(m, n_images, row_offsets_host);
 }
@@ -298,8 +334,11 @@ int xrb_match_pairs_device(xrb_matcher *m, int n_pairs, const int32_t (*pairs_de
     if (n_pairs == 0) return XRB_OK;
     XRB_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = ensure_scratch(m, n_pairs);
-    if (rc) return rc;
+    int rc;
+    if ((rc = check_on_device(m, pairs_dev, "pairs_device: pair list"))) return rc;
+    if ((rc = check_on_device(m, counts_dev, "pairs_device: counts"))) return rc;
+    if ((rc = check_on_device(m, out_dev, "pairs_device: output"))) return rc;
+    if ((rc = ensure_scratch(m, n_pairs))) return rc;
     if (m->stream != st) XRB_CUDA(cudaStreamSynchronize(m->stream));  // scratch memsets
     if (out_stride < std::min(max_match, m->max_features)) {
         // every pair may legitimately produce min(max_match, n1) matches
@@ -362,23 +401,58 @@ int xrb_match_pairs(xrb_matcher *m, int n_pairs, const int32_t (*pairs)[2], floa
         max_n = std::max<int64_t>(max_n, m->offsets[i + 1] - m->offsets[i]);
     const int max_feat = (int)std::min<int64_t>(max_n, m->max_features);
     const int stride = std::max(1, std::min(max_match, max_feat));
-    const int chunk = m->chunk_pairs;
+    // Pipeline in chunks of <= 512 pairs: while the host drains chunk c (offsets, then the packed
+    // match list into the caller's buffer) the device is already scoring chunk c + 1.
+    const int chunk = std::min(m->chunk_pairs, 512);
     if ((rc = m->strided.reserve((size_t)chunk * stride * 8))) return rc;
     if ((rc = m->packed.reserve((size_t)chunk * stride * 8))) return rc;
+    if ((rc = m->packed2.reserve((size_t)chunk * stride * 8))) return rc;
+    if ((rc = m->pack_offsets2.reserve((size_t)(m->chunk_pairs + 1) * 8))) return rc;
     if ((rc = m->pair_idx.reserve((size_t)chunk * 8))) return rc;
+    if (!m->copy_stream) {
+        XRB_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            XRB_CUDA(cudaEventCreateWithFlags(&m->ev_off[b], cudaEventDisableTiming));
+            XRB_CUDA(cudaEventCreateWithFlags(&m->ev_copied[b], cudaEventDisableTiming));
+        }
+    }
+    if (m->h_off_cap < (size_t)chunk + 1) {
+        for (int b = 0; b < 2; ++b) {
+            if (m->h_off[b]) cudaFreeHost(m->h_off[b]);
+            m->h_off[b] = nullptr;
+            XRB_CUDA(cudaMallocHost(&m->h_off[b], ((size_t)chunk + 1) * 8));
+        }
+        m->h_off_cap = (size_t)chunk + 1;
+    }
     if (launch_vlow(distmax, ratiomax, m->vlow.as<int>(), st)) return XRB_ERR_CUDA;
 
-    std::vector<int64_t> chunk_off(chunk + 1);
     int64_t total = 0;
     bool overflow = false;
-    for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
-        const int n = std::min(chunk, n_pairs - p0);
-        XRB_CUDA(cudaMemcpyAsync(m->pair_idx.p, pairs + p0, (size_t)n * 8,
-                                 cudaMemcpyHostToDevice, st));
+    DevBuf *packed[2] = {&m->packed, &m->packed2}, *poff[2] = {&m->pack_offsets, &m->pack_offsets2};
+    auto drain = [&](int c) -> int {  // host side of chunk c: offsets, then the D2H of its matches
+        const int b = c & 1, p0 = c * chunk, n = std::min(chunk, n_pairs - p0);
+        XRB_CUDA(cudaEventSynchronize(m->ev_off[b]));
+        const int64_t got = m->h_off[b][n];
+        for (int k = 0; k < n; ++k) out_offsets[p0 + k + 1] = total + m->h_off[b][k + 1];
+        if (total + got <= out_capacity && out) {
+            if (got)
+                XRB_CUDA(cudaMemcpyAsync(out + total, packed[b]->p, (size_t)got * 8, cudaMemcpyDeviceToHost,
+                                         m->copy_stream));
+        } else {
+            overflow = true;
+        }
+        XRB_CUDA(cudaEventRecord(m->ev_copied[b], m->copy_stream));
+        total += got;
+        return XRB_OK;
+    };
+    const int n_chunks = (n_pairs + chunk - 1) / chunk;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b = c & 1, p0 = c * chunk, n = std::min(chunk, n_pairs - p0);
+        if (c >= 2) XRB_CUDA(cudaStreamWaitEvent(st, m->ev_copied[b], 0));  // packed[b] is free again
+        XRB_CUDA(cudaMemcpyAsync(m->pair_idx.p, pairs + p0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
         PairDesc *pd = m->pairdesc.as<PairDesc>();
-        if ((rc = launch_build_pairs(m->pair_idx.as<int32_t[2]>(), n,
-                                     m->offsets_dev.as<int64_t>(), m->block, m->max_features,
-                                     pd, st)))
+        if ((rc = launch_build_pairs(m->pair_idx.as<int32_t[2]>(), n, m->offsets_dev.as<int64_t>(), m->block,
+                                     m->max_features, pd, st)))
             return rc;
         if (use_fused(m, max_feat)) {
             if ((rc = match_fused(m, pd, n, false, distmax, ratiomax, mutual_best_match, max_match,
@@ -391,23 +465,14 @@ int xrb_match_pairs(xrb_matcher *m, int n_pairs, const int32_t (*pairs)[2], floa
                 return rc;
         }
         if ((rc = launch_pack(m->counts.as<int32_t>(), n, m->strided.as<uint32_t[2]>(), stride,
-                              m->pack_offsets.as<int64_t>(), m->packed.as<uint32_t[2]>(), 0,
-                              (int64_t)chunk * stride, st)))
+                              poff[b]->as<int64_t>(), packed[b]->as<uint32_t[2]>(), 0, (int64_t)chunk * stride, st)))
             return rc;
-        XRB_CUDA(cudaMemcpyAsync(chunk_off.data(), m->pack_offsets.p, (size_t)(n + 1) * 8,
-                                 cudaMemcpyDeviceToHost, st));
-        XRB_CUDA(cudaStreamSynchronize(st));
-        const int64_t got = chunk_off[n];
-        for (int k = 0; k < n; ++k) out_offsets[p0 + k + 1] = total + chunk_off[k + 1];
-        if (total + got <= out_capacity && out) {
-            if (got)
-                XRB_CUDA(cudaMemcpyAsync(out + total, m->packed.p, (size_t)got * 8,
-                                         cudaMemcpyDeviceToHost, st));
-        } else {
-            overflow = true;
-        }
-        total += got;
+        XRB_CUDA(cudaMemcpyAsync(m->h_off[b], poff[b]->p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+        XRB_CUDA(cudaEventRecord(m->ev_off[b], st));
+        if (c >= 1 && (rc = drain(c - 1))) return rc;
     }
+    if ((rc = drain(n_chunks - 1))) return rc;
+    XRB_CUDA(cudaStreamSynchronize(m->copy_stream));
     XRB_CUDA(cudaStreamSynchronize(st));
     if (overflow) {
         set_error("match_pairs: out_capacity %lld < %lld matches", (long long)out_capacity,
