@@ -241,6 +241,12 @@ int xrb_ba_residuals(xrb_ba_solver *s, double *out_residuals);
  * [5] whole run; and launches of each (same indices). */
 int xrb_ba_profile(const xrb_ba_solver *s, double ms[6], int64_t launches[6]);
 
+/* Debug hook (no reference counterpart): timeline of the Cholesky kernels of the next solves.
+ * enable != 0 arms the recorder; enable == 0 stops it and copies up to cap_records records of
+ * 12 int64 words {kernel id, step, t_begin ns, t_end ns, 8 phase cycle counts}; returns the
+ * number of records (or a negative status). */
+int xrb_debug_chol_trace(int enable, int64_t *out, int cap_records);
+
 /* Finer split of the last run, out[n >= 8]: [0..2] total ms of k_lin (+ memsets), k_gather,
  * k_cam_blocks; [3] linear solves executed; [4] off-diagonal 6x6 blocks of the reduced camera
  * system; [5] (block, point) incidences the gather walks; [6] reduced system dimension;

@@ -94,6 +94,7 @@ SIGNATURES = {
     "xrb_ba_residuals": (C.c_int, [C.c_void_p, C.c_void_p]),
     "xrb_ba_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "xrb_ba_profile_detail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "xrb_debug_chol_trace": (C.c_int, [C.c_int, C.c_void_p, C.c_int]),
 }
 
 

@@ -651,6 +651,12 @@ int xrb_ba_residuals(xrb_ba_solver *s, double *out) {
     return rc;
 }
 
+/* debug hook (not part of the reference surface): timeline of the Cholesky kernels */
+int xrb_debug_chol_trace(int enable, int64_t *out, int cap_records) {
+    static_assert(sizeof(long long) == sizeof(int64_t), "");
+    return ba_chol_trace(enable, reinterpret_cast<long long *>(out), cap_records);
+}
+
 int xrb_ba_profile_detail(const xrb_ba_solver *s, double *out, int n) {
     if (!s || !out || n < 8) return XRB_ERR_INVALID;
     out[0] = s->ms_kernel[0], out[1] = s->ms_kernel[1], out[2] = s->ms_kernel[2];

@@ -13,6 +13,7 @@
 // graph.  Roofline: FP64 FMA pipe (64 FMA/clk/SM); see DESIGN.md §B.4.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <map>
 #include <tuple>
 #include <vector>
@@ -22,6 +23,36 @@
 namespace xrb {
 
 constexpr int NB = 64;  // block-column width == GEMM depth
+
+// ---- optional timeline (xrb_debug_chol_trace): when switched on, CTA 0 of every kernel of the
+// factorisation records (kernel id, step, %globaltimer at entry/exit) and the fused diagonal
+// CTA also its phase cycle counts.  Off by default: one predicated load per kernel.
+constexpr int kTraceCap = 4096, kTraceWords = 12;
+__device__ int g_trace_on = 0;
+__device__ unsigned int g_trace_n = 0;
+__device__ long long g_trace[kTraceCap * kTraceWords];
+
+__device__ __forceinline__ long long gtimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct Trace {  // lives in thread 0 of the recording CTA
+    long long t0 = 0, ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool on = false;
+    __device__ void begin(bool recorder) {
+        on = recorder && g_trace_on != 0;
+        if (on) t0 = gtimer();
+    }
+    __device__ void end(int id, int step) {
+        if (!on) return;
+        const unsigned slot = atomicAdd(&g_trace_n, 1u);
+        if (slot >= (unsigned)kTraceCap) return;
+        long long *r = g_trace + (size_t)slot * kTraceWords;
+        r[0] = id, r[1] = step, r[2] = t0, r[3] = gtimer();
+        for (int i = 0; i < 8; ++i) r[4 + i] = ph[i];
+    }
+};
 
 // ---- 1. diagonal block ---------------------------------------------------------------------
 // 64 x 64 Cholesky + inverse in one CTA (256 threads), blocked by 16:
@@ -36,41 +67,76 @@ constexpr int kDiagSmem = (2 * NB * (NB + 1) + NB * (SB + 1)) * (int)sizeof(doub
 
 // In-place factorisation of the 64 x 64 block held in shared memory A (lower part, rows >= kb
 // made identity by the caller); on return A holds L and X holds L^-1.  256 threads.
-__device__ void diag_factor(double (*A)[NB + 1], double (*X)[NB + 1], double (*T)[SB + 1], double *__restrict__ fail) {
+// 16 x 16 factor and inverse of one warp, entirely in registers.  The loops are spelled as
+// template recursion: with `#pragma unroll` the compiler kept the triangular inner loops rolled,
+// which put a[] and x[] in local memory and made this serial section 5x slower (r01 trace:
+// 14 k cycles per 16-block, 57 % of the fused diagonal CTA).
+template <int J, int C>
+__device__ __forceinline__ void fac_upd(double (&a)[SB], const int rl) {
+    if constexpr (C < SB) {
+        const double lcj = __shfl_sync(0xFFFFFFFFu, a[J], C);  // L[C][J]
+        if (rl >= C) a[C] = fma(-a[J], lcj, a[C]);
+        fac_upd<J, C + 1>(a, rl);
+    }
+}
+template <int J>
+__device__ __forceinline__ void fac_col(double (&a)[SB], const int rl, double &inv_mine, bool &bad) {
+    if constexpr (J < SB) {
+        double d = __shfl_sync(0xFFFFFFFFu, a[J], J);
+        if (!(d > 0.0) || !isfinite(d)) bad = true, d = 1.0;
+        // the 64 pivots are a serial chain: rsqrt + multiplies instead of the much longer
+        // software sqrt and divide sequences
+        const double inv = rsqrt(d);
+        if (rl == J) inv_mine = inv;
+        a[J] = rl == J ? d * inv : a[J] * inv;  // L[r][J] for r >= J
+        fac_upd<J, J + 1>(a, rl);
+        fac_col<J + 1>(a, rl, inv_mine, bad);
+    }
+}
+template <int R, int P>
+__device__ __forceinline__ void inv_dot(const double (&a)[SB], const double (&x)[SB], double &v0, double &v1) {
+    if constexpr (P < R) {
+        const double l = __shfl_sync(0xFFFFFFFFu, a[P], R);  // L[R][P]
+        if constexpr ((P & 1) != 0)
+            v1 = fma(-l, x[P], v1);
+        else
+            v0 = fma(-l, x[P], v0);
+        inv_dot<R, P + 1>(a, x, v0, v1);
+    }
+}
+template <int R>
+__device__ __forceinline__ void inv_row(const double (&a)[SB], double (&x)[SB], const int rl, const double inv_mine) {
+    if constexpr (R < SB) {  // lane rl owns column rl of the inverse: x[R] = X[R][rl]
+        double v0 = rl == R ? 1.0 : 0.0, v1 = 0.0;
+        inv_dot<R, 0>(a, x, v0, v1);
+        x[R] = (v0 + v1) * __shfl_sync(0xFFFFFFFFu, inv_mine, R);
+        inv_row<R + 1>(a, x, rl, inv_mine);
+    }
+}
+
+__device__ void diag_factor(double (*A)[NB + 1], double (*X)[NB + 1], double (*T)[SB + 1], double *__restrict__ fail,
+                            Trace *tr = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ti = tid >> 4, tj = tid & 15;
     bool bad = false;
+    const bool tron = tr && tr->on;  // phase cycles: ph[1] warp factor, ph[2] panel, ph[3] trailing, ph[4] inverse
+    long long tc = tron ? clock64() : 0;
+#define XRB_TRACE_PHASE(k)                    \
+    if (tron) {                               \
+        const long long now = clock64();      \
+        tr->ph[k] += now - tc, tc = now;      \
+    }
     for (int b = 0; b < NB; b += SB) {
         if (warp == 0) {
-            // ---- 16 x 16 factor: lane l (< 16) owns row b + l
+            // ---- 16 x 16 factor: lane l (< 16) owns row b + l (lanes 16..31 mirror them)
             const int rl = lane & 15;
-            double a[SB];
+            double a[SB], x[SB];
 #pragma unroll
             for (int c = 0; c < SB; ++c) a[c] = A[b + rl][b + c];
             double inv_mine = 1.0;  // 1 / L[rl][rl]
-#pragma unroll
-            for (int j = 0; j < SB; ++j) {
-                double d = __shfl_sync(0xFFFFFFFFu, a[j], j);
-                if (!(d > 0.0) || !isfinite(d)) bad = true, d = 1.0;
-                // the 64 pivots are a serial chain: rsqrt + multiplies instead of the much
-                // longer software sqrt and divide sequences
-                const double inv = rsqrt(d);
-                if (rl == j) inv_mine = inv;
-                a[j] = rl == j ? d * inv : a[j] * inv;  // L[r][j] for r >= j
-#pragma unroll
-                for (int c = j + 1; c < SB; ++c) {
-                    const double lcj = __shfl_sync(0xFFFFFFFFu, a[j], c);
-                    if (rl >= c) a[c] = fma(-a[j], lcj, a[c]);
-                }
-            }
+            fac_col<0>(a, rl, inv_mine, bad);
             // ---- its inverse: lane l owns column l; L[r][p] broadcast from lane r
-            double x[SB];
-#pragma unroll
-            for (int r = 0; r < SB; ++r) {
-                double v = rl == r ? 1.0 : 0.0;
-#pragma unroll
-                for (int p = 0; p < r; ++p) v = fma(-__shfl_sync(0xFFFFFFFFu, a[p], r), x[p], v);
-                x[r] = v * __shfl_sync(0xFFFFFFFFu, inv_mine, r);
-            }
+            inv_row<0>(a, x, rl, inv_mine);
             if (lane < SB) {
 #pragma unroll
                 for (int c = 0; c < SB; ++c) {
@@ -80,6 +146,7 @@ __device__ void diag_factor(double (*A)[NB + 1], double (*X)[NB + 1], double (*T
             }
         }
         __syncthreads();
+        XRB_TRACE_PHASE(1)
         const int below = NB - b - SB;  // rows under the sub-block
         if (below > 0) {
             // ---- panel: P[i][c] = sum_{p <= c} A[i][b+p] * Xbb[c][p]   (= A_panel * Lbb^-T)
@@ -97,44 +164,93 @@ __device__ void diag_factor(double (*A)[NB + 1], double (*X)[NB + 1], double (*T
                 A[i][b + c] = T[i][c];
             }
             __syncthreads();
-            // ---- trailing update: A[i][j] -= sum_p A[i][b+p] A[j][b+p], j <= i
-            for (int idx = tid; idx < below * below; idx += 256) {
-                const int i = b + SB + idx / below, j = b + SB + idx % below;
-                if (j > i) continue;
-                double v = 0.0;
+            XRB_TRACE_PHASE(2)
+            // ---- trailing update A[i][j] -= sum_p A[i][b+p] A[j][b+p], j <= i: thread (ti, tj) owns
+            // the lattice rows ti + 16 u, columns tj + 16 v (v <= u), a 3 x 3 register block at most
+            const int base = b + SB, nb16 = below / SB;
+            double acc[3][3] = {};
+#pragma unroll 4
+            for (int p = 0; p < SB; ++p) {
+                double ai[3], aj[3];
 #pragma unroll
-                for (int p = 0; p < SB; ++p) v = fma(A[i][b + p], A[j][b + p], v);
-                A[i][j] -= v;
+                for (int u = 0; u < 3; ++u) {
+                    ai[u] = u < nb16 ? A[base + ti + 16 * u][b + p] : 0.0;
+                    aj[u] = u < nb16 ? A[base + tj + 16 * u][b + p] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 3; ++u)
+#pragma unroll
+                    for (int v = 0; v <= u; ++v) acc[u][v] = fma(ai[u], aj[v], acc[u][v]);
             }
+            // (reads touch columns b .. b+15 only, the writes columns >= b+16: no barrier between)
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+#pragma unroll
+                for (int v = 0; v <= u; ++v) {
+                    const int i = ti + 16 * u, jj = tj + 16 * v;
+                    if (u < nb16 && jj <= i) A[base + i][base + jj] -= acc[u][v];
+                }
             __syncthreads();
+            XRB_TRACE_PHASE(3)
         }
     }
     if (bad && tid == 0) *fail = 1.0;
-    // ---- off-diagonal 16-blocks of X = L^-1, by block distance d: X_ij = -X_ii * sum_k L_ik X_kj
-    for (int d = 1; d < NB / SB; ++d) {
-        const int nblk = NB / SB - d;  // blocks (i, j = i - d), i = d .. 3
-        for (int idx = tid; idx < nblk * SB * SB; idx += 256) {
-            const int bi = d + idx / (SB * SB), r = (idx >> 4) & 15, c = idx & 15, bj = bi - d;
-            double v = 0.0;
-            for (int k = bj; k < bi; ++k)
+    // ---- off-diagonal 16-blocks of X = L^-1 by recursive doubling:
+    //   level 1: X10 = -X11 (L10 X00) and X32 = -X33 (L32 X22), two independent 16-block merges
+    //   level 2: X[32:64, 0:32] = -X_BB (L_BA X_AA) with the completed 32 x 32 triangles
+    {
+        // level 1, T1[s][r][c] = sum_p L[o1 + r][o0 + p] X[o0 + p][o0 + c], o0 = 32 s, o1 = o0 + 16
+        const int s = tid >> 7, r = (tid & 127) >> 4, c = tj, o0 = 32 * s, o1 = o0 + 16;
+        double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-                for (int p = 0; p < SB; ++p) v = fma(A[bi * SB + r][k * SB + p], X[k * SB + p][bj * SB + c], v);
-            T[(bi - d) * SB + r][c] = v;  // one 16-row slab of T per block of this distance
+        for (int p = 0; p < SB; ++p) {
+            const double xv = X[o0 + p][o0 + c];
+            t0 = fma(A[o1 + r][o0 + p], xv, t0);
+            t1 = fma(A[o1 + r + 8][o0 + p], xv, t1);
         }
+        T[16 * s + r][c] = t0, T[16 * s + r + 8][c] = t1;
         __syncthreads();
-        for (int idx = tid; idx < nblk * SB * SB; idx += 256) {
-            const int bi = d + idx / (SB * SB), r = (idx >> 4) & 15, c = idx & 15, bj = bi - d;
-            double v = 0.0;
+        double x0 = 0.0, x1 = 0.0;
 #pragma unroll
-            for (int p = 0; p < SB; ++p)
-                if (p <= r) v = fma(X[bi * SB + r][bi * SB + p], T[(bi - d) * SB + p][c], v);
-            X[bi * SB + r][bj * SB + c] = -v;
+        for (int p = 0; p < SB; ++p) {
+            const double tv = T[16 * s + p][c];
+            x0 = fma(X[o1 + r][o1 + p], tv, x0);
+            x1 = fma(X[o1 + r + 8][o1 + p], tv, x1);
         }
-        __syncthreads();
+        X[o1 + r][o0 + c] = -x0, X[o1 + r + 8][o0 + c] = -x1;  // block (1, 0): nobody reads it in this phase
     }
+    __syncthreads();
+    {
+        // level 2: 2 x 2 register block per thread, rows ti and ti + 16, columns tj and tj + 16
+        double *T2 = &T[0][0];  // viewed as [32][33]
+        constexpr int L2 = 33, H = 32;
+        double t[2][2] = {};
+#pragma unroll 4
+        for (int p = 0; p < H; ++p) {
+            const double l0 = A[H + ti][p], l1 = A[H + ti + 16][p];
+            const double x0 = X[p][tj], x1 = X[p][tj + 16];
+            t[0][0] = fma(l0, x0, t[0][0]), t[0][1] = fma(l0, x1, t[0][1]);
+            t[1][0] = fma(l1, x0, t[1][0]), t[1][1] = fma(l1, x1, t[1][1]);
+        }
+        T2[ti * L2 + tj] = t[0][0], T2[ti * L2 + tj + 16] = t[0][1];
+        T2[(ti + 16) * L2 + tj] = t[1][0], T2[(ti + 16) * L2 + tj + 16] = t[1][1];
+        __syncthreads();
+        double y[2][2] = {};
+#pragma unroll 4
+        for (int p = 0; p < H; ++p) {
+            const double b0 = X[H + ti][H + p], b1 = X[H + ti + 16][H + p];
+            const double t0 = T2[p * L2 + tj], t1 = T2[p * L2 + tj + 16];
+            y[0][0] = fma(b0, t0, y[0][0]), y[0][1] = fma(b0, t1, y[0][1]);
+            y[1][0] = fma(b1, t0, y[1][0]), y[1][1] = fma(b1, t1, y[1][1]);
+        }
+        X[H + ti][tj] = -y[0][0], X[H + ti][tj + 16] = -y[0][1];
+        X[H + ti + 16][tj] = -y[1][0], X[H + ti + 16][tj + 16] = -y[1][1];
+    }
+    __syncthreads();
+    XRB_TRACE_PHASE(4)
+#undef XRB_TRACE_PHASE
 }
 
-// write L (lower, real rows) back into S and the inverse into its slot
 __device__ void diag_store(double (*A)[NB + 1], double (*X)[NB + 1], double *__restrict__ S, int ld, int k0, int kb,
                            double *__restrict__ linv_out) {
     for (int idx = threadIdx.x; idx < NB * NB; idx += 256) {
@@ -157,8 +273,11 @@ chol_diag(double *__restrict__ S, int ld, int k0, int kb, double *__restrict__ l
         X[r][c] = 0.0;
     }
     __syncthreads();
-    diag_factor(A, X, T, fail);
+    Trace tr;
+    tr.begin(threadIdx.x == 0);
+    diag_factor(A, X, T, fail, &tr);
     diag_store(A, X, S, ld, k0, kb, linv_out);
+    tr.end(0, k0);
 }
 
 // ---- FP64 GEMM tile: acc[i][j] = sum_p X[row(ty,i)][p] * Y[col(tx,j)][p], p < 64 -------------
@@ -228,6 +347,8 @@ chol_panel(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int r
            const double *__restrict__ linv) {
     using T = Tile<64, 64>;  // 64-row tiles: twice the CTAs of a 128-row split, half the latency
     extern __shared__ __align__(16) double smem_d[];
+    Trace tr;
+    tr.begin(threadIdx.x == 0 && blockIdx.x == 0);
     double *Xs = smem_d, *Ys = smem_d + NB * T::LDX;
     int row0 = r0 + blockIdx.x * 64;
     int nrows = min(64, r1 - row0);
@@ -245,6 +366,7 @@ chol_panel(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int r
             const int r = ty + 16 * i, c = tx + 16 * j;
             if (r < nrows && c < kb) S[(size_t)(row0 + r) * ld + k0 + c] = acc[i][j];
         }
+    tr.end(1, k0);
 }
 
 // ---- 3. trailing update: A_ij -= L_ik L_jk^T for tiles j <= i inside the band ----------------
@@ -301,6 +423,9 @@ chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int 
     double *Ys = smem_d + 2 * KC * C::LDT;    // [2][KC][LDT]
     const int ntile = (r1 - r0 + TT - 1) / TT;
     const int ti = blockIdx.y, tj = blockIdx.x + tj_lo;  // tile-column range [tj_lo, tj_lo + gridDim.x)
+    Trace tr;
+    tr.begin(threadIdx.x == 0 && blockIdx.x == 0 && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1));
+    long long tc = tr.on ? clock64() : 0;
     int row0, nrows;
     if (ti < ntile) {
         if (tj > ti) return;
@@ -349,6 +474,7 @@ chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int 
     // C -= acc: a whole row of the register block is loaded before anything is stored, so the
     // RM loads of a row are in flight together (a load/subtract/store chain per element
     // exposes one L2 round trip per element: that was 60 % of this kernel's stall samples).
+    if (tr.on) tr.ph[0] = clock64() - tc, tc = clock64();
     const bool diag_tile = (ti < ntile) && (ti == tj);
     const bool fuse = TT == 64 && fuse_linv != nullptr && ti == 0 && tj == 0;
     double(*FA)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d);  // aliases the operand stage
@@ -378,9 +504,15 @@ chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int 
         double(*FT)[SB + 1] = reinterpret_cast<double(*)[SB + 1]>(smem_d + 2 * NB * (NB + 1));
         for (int idx = threadIdx.x; idx < NB * NB; idx += 256) FX[idx >> 6][idx & 63] = 0.0;
         __syncthreads();
-        diag_factor(FA, FX, FT, fail);
+        if (tr.on) tr.ph[5] = clock64() - tc, tc = clock64();
+        diag_factor(FA, FX, FT, fail, &tr);
+        if (tr.on) tc = clock64();
         diag_store(FA, FX, S, ld, r0, nrows, fuse_linv);
+        if (tr.on) tr.ph[6] = clock64() - tc;
+        tr.end(4, k0);
+        return;
     }
+    tr.end(TT == 64 ? 3 : 2, k0);
 }
 
 // ---- 4. backward substitution L^T x = y, kBackGroup block columns per launch ------------------
@@ -421,6 +553,8 @@ chol_backsolve(const double *__restrict__ S, int ld, int n, int blk_hi, int nblk
     __shared__ double red[4][NB];
     __shared__ double yt[NB];
     const int tid = threadIdx.x, c = tid & 63, q = tid >> 6;
+    Trace tr;
+    tr.begin(tid == 0 && blockIdx.x == 0);
     for (int g = 0; g < nblk_group; ++g) {
         const int k0 = (blk_hi - g) * NB, kb = min(NB, n - k0);
         // correction from the blocks of the group already solved: quarter q handles block gp = q
@@ -459,6 +593,7 @@ chol_backsolve(const double *__restrict__ S, int ld, int n, int blk_hi, int nblk
     red[q][c] = part;
     __syncthreads();
     if (tid < NB && j < k_low) y[j] -= red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+    tr.end(5, blk_hi);
 }
 
 namespace {
@@ -621,6 +756,25 @@ int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, dou
     g_launches.fetch_add((uint64_t)nl, std::memory_order_relaxed);
     if (launches) *launches += nl;
     return XRB_OK;
+}
+
+int ba_chol_trace(int enable, long long *out, int cap_records) {
+    int n = 0;
+    if (enable) {
+        const int one = 1;
+        const unsigned zero = 0;
+        XRB_CUDA(cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero)));
+        XRB_CUDA(cudaMemcpyToSymbol(g_trace_on, &one, sizeof(one)));
+        return 0;
+    }
+    const int off = 0;
+    unsigned cnt = 0;
+    XRB_CUDA(cudaDeviceSynchronize());
+    XRB_CUDA(cudaMemcpyToSymbol(g_trace_on, &off, sizeof(off)));
+    XRB_CUDA(cudaMemcpyFromSymbol(&cnt, g_trace_n, sizeof(cnt)));
+    n = (int)std::min<unsigned>(cnt, (unsigned)std::min(cap_records, kTraceCap));
+    if (n && out) XRB_CUDA(cudaMemcpyFromSymbol(out, g_trace, (size_t)n * kTraceWords * sizeof(long long)));
+    return n;
 }
 
 }  // namespace xrb

@@ -110,4 +110,7 @@ int ba_launch_residuals(const BAProblemDev &P, const BAStateDev &x, const BACons
 int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, double *x_out,
                              double *fail_flag, cudaStream_t st, int64_t *launches);
 
+// debug timeline of the factorisation kernels (xrb_debug_chol_trace); 12 int64 words per record
+int ba_chol_trace(int enable, long long *out, int cap_records);
+
 }  // namespace xrb
