@@ -74,8 +74,10 @@ constexpr int kDiagSmem = (2 * NB * (NB + 1) + NB * (SB + 1)) * (int)sizeof(doub
 template <int J, int C>
 __device__ __forceinline__ void fac_upd(double (&a)[SB], const int rl) {
     if constexpr (C < SB) {
+        // applied on every lane: rows above C only collect values nobody reads (the entries
+        // right of a row's diagonal), which saves the two FSELs a predicated update costs
         const double lcj = __shfl_sync(0xFFFFFFFFu, a[J], C);  // L[C][J]
-        if (rl >= C) a[C] = fma(-a[J], lcj, a[C]);
+        a[C] = fma(-a[J], lcj, a[C]);
         fac_upd<J, C + 1>(a, rl);
     }
 }
@@ -88,7 +90,7 @@ __device__ __forceinline__ void fac_col(double (&a)[SB], const int rl, double &i
         // software sqrt and divide sequences
         const double inv = rsqrt(d);
         if (rl == J) inv_mine = inv;
-        a[J] = rl == J ? d * inv : a[J] * inv;  // L[r][J] for r >= J
+        a[J] *= inv;  // L[r][J] for r >= J (lane J holds d itself: d * inv = sqrt(d))
         fac_upd<J, J + 1>(a, rl);
         fac_col<J + 1>(a, rl, inv_mine, bad);
     }
