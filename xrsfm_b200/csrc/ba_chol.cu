@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <tuple>
 #include <vector>
@@ -63,7 +64,8 @@ struct Trace {  // lives in thread 0 of the recording CTA
 //   X_ij = -X_ii (sum_k L_ik X_kj).
 // ~13 barriers in total instead of 128 (one per column) in the unblocked form.
 constexpr int SB = 16;
-constexpr int kDiagSmem = (2 * NB * (NB + 1) + NB * (SB + 1)) * (int)sizeof(double);
+constexpr int kDiagSmem = (2 * NB * (NB + 1) + NB * (SB + 1) + NB) * (int)sizeof(double);  // A, X, T, 1/diag
+__device__ int g_diag_variant = 2;  // 1: inverse of each 16-block on the chain; 2: on warp 7 (XRB_CHOL_DIAG)
 
 // In-place factorisation of the 64 x 64 block held in shared memory A (lower part, rows >= kb
 // made identity by the caller); on return A holds L and X holds L^-1.  256 threads.
@@ -114,6 +116,64 @@ __device__ __forceinline__ void inv_row(const double (&a)[SB], double (&x)[SB], 
         x[R] = (v0 + v1) * __shfl_sync(0xFFFFFFFFu, inv_mine, R);
         inv_row<R + 1>(a, x, rl, inv_mine);
     }
+}
+
+// Off-diagonal 16-blocks of X = L^-1 once the four diagonal 16-block inverses are in X.  256 threads;
+// ends with a barrier.
+__device__ void diag_inverse_levels(double (*A)[NB + 1], double (*X)[NB + 1], double (*T)[SB + 1]) {
+    const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+    // ---- off-diagonal 16-blocks of X = L^-1 by recursive doubling:
+    //   level 1: X10 = -X11 (L10 X00) and X32 = -X33 (L32 X22), two independent 16-block merges
+    //   level 2: X[32:64, 0:32] = -X_BB (L_BA X_AA) with the completed 32 x 32 triangles
+    {
+        // level 1, T1[s][r][c] = sum_p L[o1 + r][o0 + p] X[o0 + p][o0 + c], o0 = 32 s, o1 = o0 + 16
+        const int s = tid >> 7, r = (tid & 127) >> 4, c = tj, o0 = 32 * s, o1 = o0 + 16;
+        double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+        for (int p = 0; p < SB; ++p) {
+            const double xv = X[o0 + p][o0 + c];
+            t0 = fma(A[o1 + r][o0 + p], xv, t0);
+            t1 = fma(A[o1 + r + 8][o0 + p], xv, t1);
+        }
+        T[16 * s + r][c] = t0, T[16 * s + r + 8][c] = t1;
+        __syncthreads();
+        double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+        for (int p = 0; p < SB; ++p) {
+            const double tv = T[16 * s + p][c];
+            x0 = fma(X[o1 + r][o1 + p], tv, x0);
+            x1 = fma(X[o1 + r + 8][o1 + p], tv, x1);
+        }
+        X[o1 + r][o0 + c] = -x0, X[o1 + r + 8][o0 + c] = -x1;  // block (1, 0): nobody reads it in this phase
+    }
+    __syncthreads();
+    {
+        // level 2: 2 x 2 register block per thread, rows ti and ti + 16, columns tj and tj + 16
+        double *T2 = &T[0][0];  // viewed as [32][33]
+        constexpr int L2 = 33, H = 32;
+        double t[2][2] = {};
+#pragma unroll 4
+        for (int p = 0; p < H; ++p) {
+            const double l0 = A[H + ti][p], l1 = A[H + ti + 16][p];
+            const double x0 = X[p][tj], x1 = X[p][tj + 16];
+            t[0][0] = fma(l0, x0, t[0][0]), t[0][1] = fma(l0, x1, t[0][1]);
+            t[1][0] = fma(l1, x0, t[1][0]), t[1][1] = fma(l1, x1, t[1][1]);
+        }
+        T2[ti * L2 + tj] = t[0][0], T2[ti * L2 + tj + 16] = t[0][1];
+        T2[(ti + 16) * L2 + tj] = t[1][0], T2[(ti + 16) * L2 + tj + 16] = t[1][1];
+        __syncthreads();
+        double y[2][2] = {};
+#pragma unroll 4
+        for (int p = 0; p < H; ++p) {
+            const double b0 = X[H + ti][H + p], b1 = X[H + ti + 16][H + p];
+            const double t0 = T2[p * L2 + tj], t1 = T2[p * L2 + tj + 16];
+            y[0][0] = fma(b0, t0, y[0][0]), y[0][1] = fma(b0, t1, y[0][1]);
+            y[1][0] = fma(b1, t0, y[1][0]), y[1][1] = fma(b1, t1, y[1][1]);
+        }
+        X[H + ti][tj] = -y[0][0], X[H + ti][tj + 16] = -y[0][1];
+        X[H + ti + 16][tj] = -y[1][0], X[H + ti + 16][tj + 16] = -y[1][1];
+    }
+    __syncthreads();
 }
 
 __device__ void diag_factor(double (*A)[NB + 1], double (*X)[NB + 1], double (*T)[SB + 1], double *__restrict__ fail,
@@ -197,58 +257,132 @@ __device__ void diag_factor(double (*A)[NB + 1], double (*X)[NB + 1], double (*T
         }
     }
     if (bad && tid == 0) *fail = 1.0;
-    // ---- off-diagonal 16-blocks of X = L^-1 by recursive doubling:
-    //   level 1: X10 = -X11 (L10 X00) and X32 = -X33 (L32 X22), two independent 16-block merges
-    //   level 2: X[32:64, 0:32] = -X_BB (L_BA X_AA) with the completed 32 x 32 triangles
-    {
-        // level 1, T1[s][r][c] = sum_p L[o1 + r][o0 + p] X[o0 + p][o0 + c], o0 = 32 s, o1 = o0 + 16
-        const int s = tid >> 7, r = (tid & 127) >> 4, c = tj, o0 = 32 * s, o1 = o0 + 16;
-        double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-        for (int p = 0; p < SB; ++p) {
-            const double xv = X[o0 + p][o0 + c];
-            t0 = fma(A[o1 + r][o0 + p], xv, t0);
-            t1 = fma(A[o1 + r + 8][o0 + p], xv, t1);
-        }
-        T[16 * s + r][c] = t0, T[16 * s + r + 8][c] = t1;
-        __syncthreads();
-        double x0 = 0.0, x1 = 0.0;
-#pragma unroll
-        for (int p = 0; p < SB; ++p) {
-            const double tv = T[16 * s + p][c];
-            x0 = fma(X[o1 + r][o1 + p], tv, x0);
-            x1 = fma(X[o1 + r + 8][o1 + p], tv, x1);
-        }
-        X[o1 + r][o0 + c] = -x0, X[o1 + r + 8][o0 + c] = -x1;  // block (1, 0): nobody reads it in this phase
+    diag_inverse_levels(A, X, T);
+    XRB_TRACE_PHASE(4)
+#undef XRB_TRACE_PHASE
+}
+
+// ---- variant 2 of the diagonal block: the serial chain per 16-block is factor -> triangular solve
+// of the rows below -> trailing update; the inverse of the 16-block (needed only for the final
+// L^-1) runs on warp 7 next to it, off the chain.
+template <int C, int C2>
+__device__ __forceinline__ void trsm_upd(double (&a)[SB], const double x, double (*A)[NB + 1], const int b) {
+    if constexpr (C2 < SB) {
+        a[C2] = fma(-x, A[b + C2][b + C], a[C2]);  // L[C2][C]: same address on every lane (broadcast)
+        trsm_upd<C, C2 + 1>(a, x, A, b);
     }
-    __syncthreads();
-    {
-        // level 2: 2 x 2 register block per thread, rows ti and ti + 16, columns tj and tj + 16
-        double *T2 = &T[0][0];  // viewed as [32][33]
-        constexpr int L2 = 33, H = 32;
-        double t[2][2] = {};
-#pragma unroll 4
-        for (int p = 0; p < H; ++p) {
-            const double l0 = A[H + ti][p], l1 = A[H + ti + 16][p];
-            const double x0 = X[p][tj], x1 = X[p][tj + 16];
-            t[0][0] = fma(l0, x0, t[0][0]), t[0][1] = fma(l0, x1, t[0][1]);
-            t[1][0] = fma(l1, x0, t[1][0]), t[1][1] = fma(l1, x1, t[1][1]);
-        }
-        T2[ti * L2 + tj] = t[0][0], T2[ti * L2 + tj + 16] = t[0][1];
-        T2[(ti + 16) * L2 + tj] = t[1][0], T2[(ti + 16) * L2 + tj + 16] = t[1][1];
-        __syncthreads();
-        double y[2][2] = {};
-#pragma unroll 4
-        for (int p = 0; p < H; ++p) {
-            const double b0 = X[H + ti][H + p], b1 = X[H + ti + 16][H + p];
-            const double t0 = T2[p * L2 + tj], t1 = T2[p * L2 + tj + 16];
-            y[0][0] = fma(b0, t0, y[0][0]), y[0][1] = fma(b0, t1, y[0][1]);
-            y[1][0] = fma(b1, t0, y[1][0]), y[1][1] = fma(b1, t1, y[1][1]);
-        }
-        X[H + ti][tj] = -y[0][0], X[H + ti][tj + 16] = -y[0][1];
-        X[H + ti + 16][tj] = -y[1][0], X[H + ti + 16][tj + 16] = -y[1][1];
+}
+template <int C>
+__device__ __forceinline__ void trsm_col(double (&a)[SB], double (*A)[NB + 1], const double *dinv, const int b) {
+    if constexpr (C < SB) {
+        const double x = a[C] * dinv[b + C];
+        a[C] = x;
+        trsm_upd<C, C + 1>(a, x, A, b);
+        trsm_col<C + 1>(a, A, dinv, b);
     }
-    __syncthreads();
+}
+template <int R, int P>
+__device__ __forceinline__ void inv2_dot(const double (&x)[SB], double (*A)[NB + 1], const int b, double &v0, double &v1) {
+    if constexpr (P < R) {
+        const double l = A[b + R][b + P];
+        if constexpr ((P & 1) != 0)
+            v1 = fma(-l, x[P], v1);
+        else
+            v0 = fma(-l, x[P], v0);
+        inv2_dot<R, P + 1>(x, A, b, v0, v1);
+    }
+}
+template <int R>
+__device__ __forceinline__ void inv2_row(double (&x)[SB], double (*A)[NB + 1], const double *dinv, const int b, const int rl) {
+    if constexpr (R < SB) {
+        double v0 = rl == R ? 1.0 : 0.0, v1 = 0.0;
+        inv2_dot<R, 0>(x, A, b, v0, v1);
+        x[R] = (v0 + v1) * dinv[b + R];
+        inv2_row<R + 1>(x, A, dinv, b, rl);
+    }
+}
+
+__device__ void diag_factor2(double (*A)[NB + 1], double (*X)[NB + 1], double (*T)[SB + 1], double *dinv,
+                             double *__restrict__ fail, Trace *tr = nullptr) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tj = tid & 15;
+    bool bad = false;
+    const bool tron = tr && tr->on;  // ph[1] factor (+ barrier), ph[2] solve, ph[3] trailing, ph[4] inverse levels
+    long long tc = tron ? clock64() : 0;
+#define XRB_TRACE_PHASE(k)                    \
+    if (tron) {                               \
+        const long long now = clock64();      \
+        tr->ph[k] += now - tc, tc = now;      \
+    }
+    for (int b = 0; b < NB; b += SB) {
+        if (warp == 0) {
+            const int rl = lane & 15;
+            double a[SB];
+#pragma unroll
+            for (int c = 0; c < SB; ++c) a[c] = A[b + rl][b + c];
+            double inv_mine = 1.0;
+            fac_col<0>(a, rl, inv_mine, bad);
+            if (lane < SB) {
+#pragma unroll
+                for (int c = 0; c < SB; ++c)
+                    if (c <= rl) A[b + rl][b + c] = a[c];
+                dinv[b + rl] = inv_mine;
+            }
+        }
+        __syncthreads();  // warp 7 arrives here once the previous 16-block's inverse is done
+        XRB_TRACE_PHASE(1)
+        const int below = NB - b - SB;
+        if (warp == 7) {
+            // inverse of the 16-block from shared memory: lane l owns column l of X_bb
+            const int rl = lane & 15;
+            double x[SB];
+            inv2_row<0>(x, A, dinv, b, rl);
+            if (lane < SB) {
+#pragma unroll
+                for (int r = 0; r < SB; ++r) X[b + r][b + rl] = x[r];  // zero above the diagonal by construction
+            }
+        } else if (below > 0) {
+            // rows below: P = A_panel L_bb^-T by forward substitution, one thread per row, right-looking
+            if (tid < below) {
+                const int i = b + SB + tid;
+                double a[SB];
+#pragma unroll
+                for (int c = 0; c < SB; ++c) a[c] = A[i][b + c];
+                trsm_col<0>(a, A, dinv, b);
+#pragma unroll
+                for (int c = 0; c < SB; ++c) A[i][b + c] = a[c];
+            }
+            asm volatile("bar.sync 1, 224;" ::: "memory");
+            XRB_TRACE_PHASE(2)
+            // trailing update by the 224 threads of warps 0..6: rows ti + 14 u, columns tj + 16 v
+            const int base = b + SB, nb16 = below / SB, ti = tid >> 4;
+            double acc[4][3] = {};
+#pragma unroll 4
+            for (int p = 0; p < SB; ++p) {
+                double ai[4], aj[3];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ai[u] = (ti + 14 * u) < below ? A[base + ti + 14 * u][b + p] : 0.0;
+#pragma unroll
+                for (int v = 0; v < 3; ++v) aj[v] = v < nb16 ? A[base + tj + 16 * v][b + p] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) acc[u][v] = fma(ai[u], aj[v], acc[u][v]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {
+                    const int i = ti + 14 * u, jj = tj + 16 * v;
+                    if (i < below && v < nb16 && jj <= i) A[base + i][base + jj] -= acc[u][v];
+                }
+            asm volatile("bar.sync 1, 224;" ::: "memory");
+            XRB_TRACE_PHASE(3)
+        }
+    }
+    if (bad && tid == 0) *fail = 1.0;
+    __syncthreads();  // the last 16-block's inverse (warp 7) is in X
+    diag_inverse_levels(A, X, T);
     XRB_TRACE_PHASE(4)
 #undef XRB_TRACE_PHASE
 }
@@ -277,7 +411,10 @@ chol_diag(double *__restrict__ S, int ld, int k0, int kb, double *__restrict__ l
     __syncthreads();
     Trace tr;
     tr.begin(threadIdx.x == 0);
-    diag_factor(A, X, T, fail, &tr);
+    if (g_diag_variant == 2)
+        diag_factor2(A, X, T, smem_d + 2 * NB * (NB + 1) + NB * (SB + 1), fail, &tr);
+    else
+        diag_factor(A, X, T, fail, &tr);
     diag_store(A, X, S, ld, k0, kb, linv_out);
     tr.end(0, k0);
 }
@@ -411,8 +548,12 @@ __device__ __forceinline__ void upd_store(double *dst, const double2 (&v)[Update
     }
 }
 
-template <int TT>
-__global__ void __launch_bounds__(256)
+// kDeep (TT == 64, the tiles of the critical first tile column): every operand chunk and the C tile
+// are requested from L2 before anything is consumed — one exposed round trip instead of one per
+// pipeline chunk plus one for C.  The bulk tiles keep the double-buffered pipeline (less shared
+// memory and registers per CTA, more CTAs per SM).
+template <int TT, bool kDeep = false>
+__global__ void __launch_bounds__(256, (TT == 64 && !kDeep) ? 2 : 1)
 chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int rhs_row, int tj_lo,
             double *__restrict__ fuse_linv, double *__restrict__ fail) {
     // fuse_linv != nullptr (TT == 64 only): the CTA of tile (0, 0) goes on to factor the block it
@@ -440,13 +581,53 @@ chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int 
     const double *xsrc = S + (size_t)row0 * ld + k0, *ysrc = S + (size_t)col0 * ld + k0;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 
+    double acc[RM][RM] = {};
+    const bool diag_tile = (ti < ntile) && (ti == tj);
+    double cpre[kDeep ? RM : 1][kDeep ? RM : 1];
+    if constexpr (kDeep) {
+        static_assert(TT == 64, "deep prefetch is sized for 64 x 64 tiles");
+        constexpr int NC = NB / KC;
+        double2 ax[NC][C::kPerThread], ay[NC][C::kPerThread];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            upd_fetch<TT>(xsrc, (size_t)ld, nrows, kb, c * KC, ax[c]);
+            upd_fetch<TT>(ysrc, (size_t)ld, ncols, kb, c * KC, ay[c]);
+        }
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
+#pragma unroll
+            for (int j = 0; j < RM; ++j) {
+                const int r = ty + 16 * i, cc = tx + 16 * j;
+                const bool ok = r < nrows && cc < ncols && (!diag_tile || cc <= r);
+                cpre[i][j] = ok ? __ldcg(S + (size_t)(row0 + r) * ld + col0 + cc) : 0.0;
+            }
+        double *Xd = smem_d, *Yd = smem_d + NB * C::LDT;  // [64][LDT] each, p-major
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            upd_store<TT>(Xd + c * KC * C::LDT, ax[c]);
+            upd_store<TT>(Yd + c * KC * C::LDT, ay[c]);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int p = 0; p < NB; ++p) {
+            double a[RM], b[RM];
+#pragma unroll
+            for (int i = 0; i < RM; ++i) a[i] = Xd[p * C::LDT + ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < RM; ++j) b[j] = Yd[p * C::LDT + tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+#pragma unroll
+                for (int j = 0; j < RM; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();  // the stage is dead: the fused path reuses it for the diagonal block
+    } else {
     double2 vx[C::kPerThread], vy[C::kPerThread];
     upd_fetch<TT>(xsrc, (size_t)ld, nrows, kb, 0, vx);
     upd_fetch<TT>(ysrc, (size_t)ld, ncols, kb, 0, vy);
     upd_store<TT>(Xs, vx);
     upd_store<TT>(Ys, vy);
     __syncthreads();
-    double acc[RM][RM] = {};
 #pragma unroll 1
     for (int c = 0; c < NB / KC; ++c) {
         const int cur = c & 1;
@@ -473,12 +654,12 @@ chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int 
         }
         __syncthreads();
     }
+    }
     // C -= acc: a whole row of the register block is loaded before anything is stored, so the
     // RM loads of a row are in flight together (a load/subtract/store chain per element
     // exposes one L2 round trip per element: that was 60 % of this kernel's stall samples).
     if (tr.on) tr.ph[0] = clock64() - tc, tc = clock64();
-    const bool diag_tile = (ti < ntile) && (ti == tj);
-    const bool fuse = TT == 64 && fuse_linv != nullptr && ti == 0 && tj == 0;
+    const bool fuse = kDeep && fuse_linv != nullptr && ti == 0 && tj == 0;  // only the critical column fuses
     double(*FA)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d);  // aliases the operand stage
 #pragma unroll
     for (int i = 0; i < RM; ++i) {
@@ -488,26 +669,32 @@ chol_update(double *__restrict__ S, int ld, int k0, int kb, int r0, int r1, int 
         for (int j = 0; j < RM; ++j) {
             const int cc = tx + 16 * j;
             const bool ok = r < nrows && cc < ncols && (!diag_tile || cc <= r);
-            cv[j] = ok ? __ldcg(S + (size_t)(row0 + r) * ld + col0 + cc) : 0.0;
+            if constexpr (kDeep)
+                cv[j] = cpre[i][j];
+            else
+                cv[j] = ok ? __ldcg(S + (size_t)(row0 + r) * ld + col0 + cc) : 0.0;
         }
 #pragma unroll
         for (int j = 0; j < RM; ++j) {
             const int cc = tx + 16 * j;
             const bool ok = r < nrows && cc < ncols && (!diag_tile || cc <= r);
-            if (fuse) {
-                if (TT == 64) FA[r][cc] = ok ? cv[j] - acc[i][j] : (r == cc ? 1.0 : 0.0);
+            if (kDeep && fuse) {
+                if constexpr (kDeep) FA[r][cc] = ok ? cv[j] - acc[i][j] : (r == cc ? 1.0 : 0.0);
             } else if (ok) {
                 S[(size_t)(row0 + r) * ld + col0 + cc] = cv[j] - acc[i][j];
             }
         }
     }
-    if (TT == 64 && fuse) {  // block-uniform branch
+    if constexpr (kDeep) if (fuse) {  // block-uniform branch
         double(*FX)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(smem_d + NB * (NB + 1));
         double(*FT)[SB + 1] = reinterpret_cast<double(*)[SB + 1]>(smem_d + 2 * NB * (NB + 1));
         for (int idx = threadIdx.x; idx < NB * NB; idx += 256) FX[idx >> 6][idx & 63] = 0.0;
         __syncthreads();
         if (tr.on) tr.ph[5] = clock64() - tc, tc = clock64();
-        diag_factor(FA, FX, FT, fail, &tr);
+        if (g_diag_variant == 2)
+            diag_factor2(FA, FX, FT, smem_d + 2 * NB * (NB + 1) + NB * (SB + 1), fail, &tr);
+        else
+            diag_factor(FA, FX, FT, fail, &tr);
         if (tr.on) tc = clock64();
         diag_store(FA, FX, S, ld, r0, nrows, fuse_linv);
         if (tr.on) tr.ph[6] = clock64() - tc;
@@ -614,15 +801,20 @@ cudaEvent_t get_event(size_t i) {
     return g_events[i];
 }
 
-template <int TT>
+template <int TT, bool kDeep = false>
+constexpr int update_smem(bool fused) {
+    const int stage = kDeep ? 2 * NB * UpdateCfg<TT>::LDT * (int)sizeof(double) : UpdateCfg<TT>::kSmemBytes;
+    return fused && kDiagSmem > stage ? kDiagSmem : stage;
+}
+
+template <int TT, bool kDeep = false>
 void launch_update(double *S, int ld, int k0, int kb, int r0, int r1, int n, int tj_lo, int tj_hi,
                    double *fuse_linv, double *fail, cudaStream_t st) {
     const int nt = (r1 - r0 + TT - 1) / TT;
     if (tj_hi <= tj_lo) return;
     dim3 grid(tj_hi - tj_lo, nt + 1);
-    const int smem = fuse_linv ? (UpdateCfg<TT>::kSmemBytes > kDiagSmem ? UpdateCfg<TT>::kSmemBytes : kDiagSmem)
-                               : UpdateCfg<TT>::kSmemBytes;
-    chol_update<TT><<<grid, 256, smem, st>>>(S, ld, k0, kb, r0, r1, n, tj_lo, fuse_linv, fail);
+    chol_update<TT, kDeep><<<grid, 256, update_smem<TT, kDeep>(fuse_linv != nullptr), st>>>(S, ld, k0, kb, r0, r1, n, tj_lo,
+                                                                                         fuse_linv, fail);
 }
 
 int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, double *fail_flag,
@@ -657,7 +849,7 @@ int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, d
             const int kb_next = min(NB, n - r0);
             const bool fuse_ok = kblk + 1 < nblk && (r1 - r0) >= kb_next;
             double *li_next = linv + (size_t)(kblk + 1) * NB * NB;
-            launch_update<64>(S, ld, k0, kb, r0, r1, n, 0, 1, fuse_ok ? li_next : nullptr, fail_flag, st);
+            launch_update<64, true>(S, ld, k0, kb, r0, r1, n, 0, 1, fuse_ok ? li_next : nullptr, fail_flag, st);
             ++nl;
             if (!fuse_ok && kblk + 1 < nblk) {
                 chol_diag<<<1, 256, kDiagSmem, st>>>(S, ld, r0, kb_next, li_next, fail_flag);
@@ -706,16 +898,24 @@ std::map<GraphKey, GraphEntry> g_graphs;
 int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, double *x_out,
                              double *fail_flag, cudaStream_t st, int64_t *launches) {
     if (n <= 0) return XRB_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};  // per device: function attributes do not carry over
+    int dev_id = 0;
+    XRB_CUDA(cudaGetDevice(&dev_id));
+    if (dev_id < 0 || dev_id >= 64) dev_id = 0;
+    if (!attr_set[dev_id]) {
         XRB_CUDA(cudaFuncSetAttribute(chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
         XRB_CUDA(cudaFuncSetAttribute(chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Tile<64, 64>::kSmemBytes));
         XRB_CUDA(cudaFuncSetAttribute(chol_update<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      UpdateCfg<128>::kSmemBytes));
+                                      update_smem<128>(false)));
         XRB_CUDA(cudaFuncSetAttribute(chol_update<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      UpdateCfg<64>::kSmemBytes > kDiagSmem ? UpdateCfg<64>::kSmemBytes : kDiagSmem));
-        attr_set = true;
+                                      update_smem<64>(true)));
+        XRB_CUDA(cudaFuncSetAttribute(chol_update<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      update_smem<64, true>(true)));
+        const char *dv = getenv("XRB_CHOL_DIAG");
+        const int variant = (dv && atoi(dv) == 1) ? 1 : 2;
+        XRB_CUDA(cudaMemcpyToSymbol(g_diag_variant, &variant, sizeof(variant)));
+        attr_set[dev_id] = true;
     }
     // The launch sequence depends only on (n, ld, bw) and the buffers: replay it as a graph.
     const GraphKey key{S, n, ld, bw, linv, x_out, fail_flag};
