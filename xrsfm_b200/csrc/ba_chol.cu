@@ -790,7 +790,7 @@ namespace {
 // Side stream + events for the look-ahead: the bulk of the trailing update of step k runs on
 // `side` while the main stream already factors the next diagonal block and forms the next
 // panel, which only need the FIRST tile column of that update.
-cudaStream_t g_side = nullptr;
+cudaStream_t g_side = nullptr, g_side2 = nullptr;
 std::vector<cudaEvent_t> g_events;
 cudaEvent_t get_event(size_t i) {
     while (g_events.size() <= i) {
@@ -822,11 +822,21 @@ int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, d
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (!g_side) cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking);
+    if (!g_side) {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        cudaStreamCreateWithPriority(&g_side, cudaStreamNonBlocking, least);
+        cudaStreamCreateWithPriority(&g_side2, cudaStreamNonBlocking, least);
+    }
     const int nblk = (n + NB - 1) / NB;
     int64_t nl = 0;
     size_t ev = 0;
-    cudaEvent_t bulk_done = nullptr;  // completion of the previous step's bulk update
+    // Look-ahead of depth 2.  Step k (block column k factored) updates the trailing matrix in three
+    // pieces: `crit` = block column k+1 (main stream, its (0, 0) CTA factors the next diagonal
+    // block), `second` = block column k+2 (side stream 2) and `rest` = everything right of it
+    // (side stream 1, the bulk of the flops).  crit(k) only needs second(k-1); second(k) needs
+    // rest(k-1): the big update has two chain steps to finish before anybody waits for it.
+    cudaEvent_t second_done = nullptr, rest_done = nullptr;
     chol_diag<<<1, 256, kDiagSmem, st>>>(S, ld, 0, min(NB, n), linv, fail_flag);  // block 0 only
     ++nl;
     for (int kblk = 0; kblk < nblk; ++kblk) {
@@ -839,10 +849,9 @@ int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, d
         ++nl;
         cudaEvent_t panel_done = get_event(ev++);
         cudaEventRecord(panel_done, st);
-        // critical part on the main stream: the first 64 columns of the trailing matrix (the
-        // next block column), after the previous bulk whose tiles it touches; its (0, 0) CTA
-        // also factors the next diagonal block
-        if (bulk_done) cudaStreamWaitEvent(st, bulk_done, 0);
+        if (second_done) cudaStreamWaitEvent(st, second_done, 0);
+        // a band narrower than two blocks: `rest` of the previous step is empty or tiny, but the
+        // main stream must still see it before the back substitution; order it here
         if (r1 > r0) {
             // fusing needs the whole next diagonal block inside this update's row range (a band
             // narrower than one block leaves rows the update never loads)
@@ -856,9 +865,22 @@ int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, d
                 ++nl;
             }
         }
-        // bulk on the side stream: everything from column r0 + 64 on
-        bulk_done = nullptr;
-        const int b0 = r0 + NB;
+        // second: block column k+2 = tile column 1 of the 64-wide tiling anchored at r0
+        cudaEvent_t prev_rest = rest_done;
+        second_done = nullptr;
+        if (r1 > r0 + NB) {
+            cudaStreamWaitEvent(g_side2, panel_done, 0);
+            if (prev_rest) cudaStreamWaitEvent(g_side2, prev_rest, 0);
+            launch_update<64>(S, ld, k0, kb, r0, r1, n, 1, 2, nullptr, fail_flag, g_side2);
+            ++nl;
+            second_done = get_event(ev++);
+            cudaEventRecord(second_done, g_side2);
+        } else if (prev_rest) {
+            cudaStreamWaitEvent(st, prev_rest, 0);  // nothing else will order it before the main stream
+        }
+        // rest: everything from column r0 + 128 on
+        rest_done = nullptr;
+        const int b0 = r0 + 2 * NB;
         if (r1 > b0) {
             cudaStreamWaitEvent(g_side, panel_done, 0);
             const int nt128 = (r1 - b0 + 127) / 128;
@@ -867,11 +889,12 @@ int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, d
             else
                 launch_update<64>(S, ld, k0, kb, b0, r1, n, 0, (r1 - b0 + 63) / 64, nullptr, fail_flag, g_side);
             ++nl;
-            bulk_done = get_event(ev++);
-            cudaEventRecord(bulk_done, g_side);
+            rest_done = get_event(ev++);
+            cudaEventRecord(rest_done, g_side);
         }
     }
-    if (bulk_done) cudaStreamWaitEvent(st, bulk_done, 0);
+    if (second_done) cudaStreamWaitEvent(st, second_done, 0);
+    if (rest_done) cudaStreamWaitEvent(st, rest_done, 0);
     double *y = S + (size_t)n * ld;  // y = L^-1 rhs now sits in row n
     for (int hi = nblk - 1; hi >= 0; hi -= kBackGroup) {
         const int ng = min(kBackGroup, hi + 1);
@@ -924,7 +947,9 @@ int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, dou
         GraphEntry e;
         cudaGraph_t graph = nullptr;
         cudaStream_t cs = nullptr;
-        bool ok = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess &&
+        int pr_least = 0, pr_greatest = 0;  // the chain's kernels go first whenever an SM frees up
+        cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest);
+        bool ok = cudaStreamCreateWithPriority(&cs, cudaStreamNonBlocking, pr_greatest) == cudaSuccess &&
                   cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         if (ok) {
             const int rc = enqueue_all(S, n, ld, bw, linv, x_out, fail_flag, cs, &e.launches);
