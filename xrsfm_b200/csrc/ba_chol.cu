@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <tuple>
 #include <vector>
 
@@ -790,16 +791,31 @@ namespace {
 // Side stream + events for the look-ahead: the bulk of the trailing update of step k runs on
 // `side` while the main stream already factors the next diagonal block and forms the next
 // panel, which only need the FIRST tile column of that update.
-cudaStream_t g_side = nullptr, g_side2 = nullptr;
-std::vector<cudaEvent_t> g_events;
-cudaEvent_t get_event(size_t i) {
-    while (g_events.size() <= i) {
-        cudaEvent_t e;
-        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-        g_events.push_back(e);
+struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+};
+using GraphKey = std::tuple<double *, int, int, int, double *, double *, double *>;
+
+// Streams, events, function attributes and instantiated graphs belong to one device: the state is
+// kept per device id so that a process driving several GPUs (one solver each) stays correct.
+struct DevCtx {
+    cudaStream_t side = nullptr, side2 = nullptr;
+    std::vector<cudaEvent_t> events;
+    std::map<GraphKey, GraphEntry> graphs;
+    bool attr_set = false;
+    cudaEvent_t get_event(size_t i) {
+        while (events.size() <= i) {
+            cudaEvent_t e;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            events.push_back(e);
+        }
+        return events[i];
     }
-    return g_events[i];
-}
+};
+constexpr int kMaxDevices = 64;
+DevCtx g_ctx[kMaxDevices];
+std::mutex g_ctx_mutex;  // enqueueing is host work; one solve is enqueued at a time
 
 template <int TT, bool kDeep = false>
 constexpr int update_smem(bool fused) {
@@ -817,17 +833,19 @@ void launch_update(double *S, int ld, int k0, int kb, int r0, int r1, int n, int
                                                                                          fuse_linv, fail);
 }
 
-int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, double *fail_flag,
+int enqueue_all(DevCtx &ctx, double *S, int n, int ld, int bw, double *linv, double *x_out, double *fail_flag,
                 cudaStream_t st, int64_t *count) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (!g_side) {
+    if (!ctx.side) {
         int least = 0, greatest = 0;
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        cudaStreamCreateWithPriority(&g_side, cudaStreamNonBlocking, least);
-        cudaStreamCreateWithPriority(&g_side2, cudaStreamNonBlocking, least);
+        cudaStreamCreateWithPriority(&ctx.side, cudaStreamNonBlocking, least);
+        cudaStreamCreateWithPriority(&ctx.side2, cudaStreamNonBlocking, least);
     }
+    cudaStream_t g_side = ctx.side, g_side2 = ctx.side2;
+    auto get_event = [&](size_t i) { return ctx.get_event(i); };
     const int nblk = (n + NB - 1) / NB;
     int64_t nl = 0;
     size_t ev = 0;
@@ -909,23 +927,21 @@ int enqueue_all(double *S, int n, int ld, int bw, double *linv, double *x_out, d
     return cudaGetLastError() == cudaSuccess ? XRB_OK : XRB_ERR_CUDA;
 }
 
-struct GraphEntry {
-    cudaGraphExec_t exec = nullptr;
-    int64_t launches = 0;
-};
-using GraphKey = std::tuple<double *, int, int, int, double *, double *, double *>;
-std::map<GraphKey, GraphEntry> g_graphs;
-
 }  // namespace
 
 int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, double *x_out,
                              double *fail_flag, cudaStream_t st, int64_t *launches) {
     if (n <= 0) return XRB_OK;
-    static bool attr_set[64] = {};  // per device: function attributes do not carry over
     int dev_id = 0;
     XRB_CUDA(cudaGetDevice(&dev_id));
-    if (dev_id < 0 || dev_id >= 64) dev_id = 0;
-    if (!attr_set[dev_id]) {
+    if (dev_id < 0 || dev_id >= kMaxDevices) {
+        set_error("cholesky: device id %d outside [0, %d)", dev_id, kMaxDevices);
+        return XRB_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    DevCtx &ctx = g_ctx[dev_id];
+    auto &g_graphs = ctx.graphs;
+    if (!ctx.attr_set) {
         XRB_CUDA(cudaFuncSetAttribute(chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
         XRB_CUDA(cudaFuncSetAttribute(chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Tile<64, 64>::kSmemBytes));
@@ -938,7 +954,7 @@ int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, dou
         const char *dv = getenv("XRB_CHOL_DIAG");
         const int variant = (dv && atoi(dv) == 1) ? 1 : 2;
         XRB_CUDA(cudaMemcpyToSymbol(g_diag_variant, &variant, sizeof(variant)));
-        attr_set[dev_id] = true;
+        ctx.attr_set = true;
     }
     // The launch sequence depends only on (n, ld, bw) and the buffers: replay it as a graph.
     const GraphKey key{S, n, ld, bw, linv, x_out, fail_flag};
@@ -952,7 +968,7 @@ int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, dou
         bool ok = cudaStreamCreateWithPriority(&cs, cudaStreamNonBlocking, pr_greatest) == cudaSuccess &&
                   cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         if (ok) {
-            const int rc = enqueue_all(S, n, ld, bw, linv, x_out, fail_flag, cs, &e.launches);
+            const int rc = enqueue_all(ctx, S, n, ld, bw, linv, x_out, fail_flag, cs, &e.launches);
             ok = cudaStreamEndCapture(cs, &graph) == cudaSuccess && rc == XRB_OK && graph != nullptr;
         }
         if (ok) ok = cudaGraphInstantiate(&e.exec, graph, 0) == cudaSuccess;
@@ -974,7 +990,7 @@ int ba_launch_cholesky_solve(double *S, int n, int ld, int bw, double *linv, dou
         XRB_CUDA(cudaGraphLaunch(it->second.exec, st));
         nl = it->second.launches;
     } else {
-        const int rc = enqueue_all(S, n, ld, bw, linv, x_out, fail_flag, st, &nl);
+        const int rc = enqueue_all(ctx, S, n, ld, bw, linv, x_out, fail_flag, st, &nl);
         if (rc) {
             set_error("cholesky launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             return rc;

@@ -477,10 +477,12 @@ int ba_launch_schur(const BAProblemDev &P, const BAStateDev &x, const BAConsts &
                     const BALinSys &L, double inv_radius, double *scalars, cudaStream_t st) {
     if (P.n_pts_local > 0) {
         const size_t smem = sizeof(WarpStage) * kWarpsPerCta;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[64] = {};  // function attributes are per device
+        int dev_id = 0;
+        XRB_CUDA(cudaGetDevice(&dev_id));
+        if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
             XRB_CUDA(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
+            if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
         }
         k_schur<<<point_grid(P.n_pts_local), kWarpsPerCta * 32, smem, st>>>(P, x, k, L, inv_radius, scalars);
         XRB_LAUNCHED();

@@ -559,14 +559,14 @@ int launch_impl(const PairDesc *pairs_dev, int n_pairs, const uint8_t *baseA, ui
     int rc;
     if ((rc = make_map(&mapA, baseA, rowsA))) return rc;
     if ((rc = make_map(&mapB, baseB, rowsB))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        XRB_CUDA(cudaFuncSetAttribute(score_tc_kernel<kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg<kFused>::kSmemBytes));
-        attr_set = true;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
+    static bool attr_set[64] = {};  // function attributes are per device
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        XRB_CUDA(cudaFuncSetAttribute(score_tc_kernel<kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg<kFused>::kSmemBytes));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = n_pairs < sms ? n_pairs : sms;
     score_tc_kernel<kFused><<<grid, kThreads, Cfg<kFused>::kSmemBytes, st>>>(
