@@ -253,6 +253,72 @@ int xrb_debug_chol_trace(int enable, int64_t *out, int cap_records);
  * [7] its half bandwidth. */
 int xrb_ba_profile_detail(const xrb_ba_solver *s, double *out, int n);
 
+/* ------------------------------------------------------------------ */
+/* Wire formats either side of the two paths     */
+/* ------------------------------------------------------------------ */
+/* All files are the reference's raw little-endian dumps (src/utility/io_base.hpp:13-87).
+ * Every reader is two-pass: *_scan reports the sizes, the caller allocates, *_read fills
+ * flat arrays — the layouts the hot paths take, without the reference's AoS objects. */
+
+/* ftr.bin — ReadFeatures / SaveFeatures (src/utility/io_feature.hpp:37-100):
+ *   int32 n_frames; per frame: name\0, int32 n_points, n_points x {float x, y, size, angle},
+ *   n_points x 128 uint8.  names_bytes counts the terminating NULs. */
+int xrb_ftr_scan(const char *path, int32_t *n_frames, int64_t *total_points, int64_t *names_bytes);
+/* row_offsets[n_frames+1] (rows of 128 bytes), desc_block[total_points*128]; optional (may be
+ * NULL): keypoints[total_points*4], names[names_bytes] (NUL-separated), name_offsets[n_frames+1]. */
+int xrb_ftr_read(const char *path, int32_t n_frames, int64_t *row_offsets, uint8_t *desc_block,
+                 float *keypoints, char *names, int64_t *name_offsets);
+/* SaveFeatures(file, frames, with_descs = true) (run_matching.cc:31).  keypoints NULL writes
+ * zeros; names NULL writes empty names. */
+int xrb_ftr_write(const char *path, int32_t n_frames, const int64_t *row_offsets,
+                  const uint8_t *desc_block, const float *keypoints, const char *names,
+                  const int64_t *name_offsets);
+/* ftr.bin -> HBM: the descriptors of every frame become the matcher's resident images (as
+ * xrb_match_upload_packed would leave them), streamed through a small pinned staging ring; the
+ * keypoints are skipped.  Frames above max_features are clamped like SetDescriptors
+ * (SiftMatchCU.cpp:102). */
+int xrb_match_upload_ftr(xrb_matcher *m, const char *path);
+
+/* fp.bin — ReadFramePairs / SaveFramePairs (io_feature.hpp:102-147):
+ *   uint64 n_pairs; per pair: int32 id1, id2, uint64 n_matches, n_matches x Match{int32 id1,
+ *   int32 id2, float64 distance}, float64 E[9] (column-major), int32 inlier_num,
+ *   n_matches x char inlier_mask.  Like the reference's reader (:120-126), pairs with
+ *   id1 == id2 are dropped: scan and read do not count them. */
+int xrb_fp_scan(const char *path, int64_t *n_pairs, int64_t *total_matches);
+/* ids[n_pairs][2], offsets[n_pairs+1], matches[total][2]; optional: distances[total],
+ * E[9*n_pairs], inlier_num[n_pairs], inlier_mask[total]. */
+int xrb_fp_read(const char *path, int64_t n_pairs, int32_t (*ids)[2], int64_t *offsets,
+                int32_t (*matches)[2], double *distances, double *E, int32_t *inlier_num,
+                char *inlier_mask);
+/* matches are the (i, j) lists xrb_match_pairs returns (same 32-bit pattern).  distances NULL
+ * -> 0.0 (Match's default, types.h:15); E NULL -> zeros (the reference leaves E unassigned on
+ * the fundamental-matrix path); inlier_mask NULL -> all 1; inlier_num NULL -> number of 1s. */
+int xrb_fp_write(const char *path, int64_t n_pairs, const int32_t (*ids)[2], const int64_t *offsets,
+                 const int32_t (*matches)[2], const double *distances, const double *E,
+                 const int32_t *inlier_num, const char *inlier_mask);
+
+/* COLMAP-style model — ReadColMapDataBinary / WriteColMapDataBinary (src/utility/io_ecim.cc:9-87,
+ * 145-232): cameras.bin, images.bin, points3D.bin under dir (dir must end with '/', the
+ * reference concatenates).  The model is flattened straight into an xrb_ba_problem exactly as
+ * BASolver::SetUp would walk it (ba_solver.cc:330-356): one observation per (frame, p2d) whose
+ * track id is present in points3D.bin, frames in file order, p2d in order. */
+typedef struct xrb_colmap_sizes {
+    int32_t n_cameras, n_frames, n_points;
+    int64_t n_p2d;    /* 2-D points over all frames (tracked or not) */
+    int64_t n_obs;    /* observations the BA problem will hold */
+} xrb_colmap_sizes;
+int xrb_colmap_scan(const char *dir, xrb_colmap_sizes *sizes);
+/* prob's arrays must be allocated for the scanned sizes (n_cams = n_frames, n_pts = n_points,
+ * n_obs, n_intr = n_cameras; the *_fixed arrays are left untouched).  Optional outputs:
+ * frame_ids[n_frames], camera_ids[n_cameras], track_ids[n_points], obs_p2d[n_obs]. */
+int xrb_colmap_read_problem(const char *dir, const xrb_colmap_sizes *sizes, xrb_ba_problem *prob,
+                            int32_t *frame_ids, int32_t *camera_ids, uint64_t *track_ids,
+                            int32_t *obs_p2d);
+/* Copy the model dir_in -> dir_out with the poses and points of prob (same order as
+ * xrb_colmap_read_problem produced): what WriteColMapDataBinary would write after the BA. */
+int xrb_colmap_write_updated(const char *dir_in, const char *dir_out, const xrb_colmap_sizes *sizes,
+                             const xrb_ba_problem *prob);
+
 #ifdef __cplusplus
 }
 #endif

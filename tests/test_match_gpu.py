@@ -190,6 +190,37 @@ def test_pipelined_chunks_keep_pair_order_and_offsets(matcher):
     np.testing.assert_array_equal(mm2, mm[: off[700]])
 
 
+def test_ftr_file_to_hbm_matches_like_uploaded_images(tmp_path, matcher):
+    """ftr.bin -> HBM (xrb_match_upload_ftr, pinned staging ring) -> batched matching -> fp.bin:
+    same match lists as the in-memory upload, and the file the reference's reader expects."""
+    from tests import io_ref
+    from xrsfm_b200 import io_formats
+    rng = np.random.default_rng(21)
+    imgs, _ = synth.make_images(5, 300, seed=13)
+    imgs = [im[: int(rng.integers(120, 301))] for im in imgs]
+    imgs[2] = imgs[2][:0]
+    frames = [dict(name=f"{i}.jpg", keypoints=rng.random((len(im), 4), dtype=np.float32), descs=im) for i, im in enumerate(imgs)]
+    path = str(tmp_path / "ftr.bin")
+    io_ref.save_features(path, frames)
+    pairs = synth.sequential_pairs(5, window=2, n_retrieval=1, seed=3)
+    matcher.set_variant(0)
+    matcher.upload_images(imgs)
+    off_a, mm_a = matcher.match_pairs(pairs)
+    matcher.upload_ftr(path)
+    off_b, mm_b = matcher.match_pairs(pairs)
+    np.testing.assert_array_equal(off_a, off_b)
+    np.testing.assert_array_equal(mm_a, mm_b)
+    out = str(tmp_path / "fp.bin")
+    io_formats.SaveFramePairs(out, pairs, off_b, mm_b)
+    back = io_ref.read_frame_pairs(out)
+    keep = [k for k, (a, b) in enumerate(pairs) if a != b]
+    assert [(p["id1"], p["id2"]) for p in back] == [tuple(pairs[k]) for k in keep]
+    for p, k in zip(back, keep):
+        assert [[i, j] for (i, j, _) in p["matches"]] == mm_b[off_b[k]: off_b[k + 1]].tolist()
+    with pytest.raises(_lib.XrbError, match="cannot open"):
+        matcher.upload_ftr(str(tmp_path / "nope.bin"))
+
+
 def test_device_pointers_must_be_device_memory():
     m = matching.SiftMatchGPU(64)
     assert m.VerifyContextGL() == 1

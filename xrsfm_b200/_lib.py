@@ -58,6 +58,11 @@ class BASummary(C.Structure):
     ]
 
 
+class ColmapSizes(C.Structure):
+    _fields_ = [("n_cameras", C.c_int32), ("n_frames", C.c_int32), ("n_points", C.c_int32),
+                ("n_p2d", C.c_int64), ("n_obs", C.c_int64)]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_void_p)
 
 # name -> (restype, argtypes); every symbol include/xrsfm_b200.h declares
@@ -95,6 +100,19 @@ SIGNATURES = {
     "xrb_ba_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "xrb_ba_profile_detail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "xrb_debug_chol_trace": (C.c_int, [C.c_int, C.c_void_p, C.c_int]),
+    "xrb_ftr_scan": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xrb_ftr_read": (C.c_int, [C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xrb_ftr_write": (C.c_int, [C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xrb_match_upload_ftr": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "xrb_fp_scan": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p]),
+    "xrb_fp_read": (C.c_int, [C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p]),
+    "xrb_fp_write": (C.c_int, [C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p]),
+    "xrb_colmap_scan": (C.c_int, [C.c_char_p, C.c_void_p]),
+    "xrb_colmap_read_problem": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
+    "xrb_colmap_write_updated": (C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p]),
 }
 
 

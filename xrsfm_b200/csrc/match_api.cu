@@ -4,6 +4,7 @@
 #include <cstring>
 #include <vector>
 
+#include "io_formats.cuh"
 #include "match_kernels.cuh"
 
 using namespace xrb;
@@ -309,6 +310,79 @@ int xrb_match_upload_packed(xrb_matcher *m, int n_images, const int64_t *row_off
                                  m->stream));
     m->block = m->images.as<uint8_t>();
     return set_offsets(m, n_images, row_offsets);
+}
+
+int xrb_match_upload_ftr(xrb_matcher *m, const char *path) {
+    if (!m || !path) {
+        set_error("upload_ftr: bad arguments");
+        return XRB_ERR_INVALID;
+    }
+    XRB_CUDA(cudaSetDevice(m->device));
+    // pass 1: frame sizes (the file is the reference's ftr.bin, io_feature.hpp:76-100)
+    std::vector<int64_t> off(1, 0);
+    int64_t max_points = 0;
+    int rc;
+    {
+        FtrReader r;
+        if ((rc = r.open(path))) return rc;
+        std::string name;
+        for (int i = 0; i < r.n_frames(); ++i) {
+            int32_t np = 0;
+            if ((rc = r.header(&name, &np)) || (rc = r.keypoints(nullptr)) || (rc = r.descriptors(nullptr))) return rc;
+            off.push_back(off.back() + np);
+            max_points = std::max<int64_t>(max_points, np);
+        }
+    }
+    const int n_images = (int)off.size() - 1;
+    if ((rc = m->images.reserve(std::max<size_t>(16, (size_t)off[n_images] * kDim)))) return rc;
+    // pass 2: descriptors file -> pinned ring -> HBM; the copy of frame i overlaps the read of i + 1
+    uint8_t *stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    const size_t stage_bytes = std::max<size_t>(16, (size_t)max_points * kDim);
+    auto cleanup = [&]() {
+        for (int b = 0; b < 2; ++b) {
+            if (done[b]) cudaEventDestroy(done[b]);
+            if (stage[b]) cudaFreeHost(stage[b]);
+        }
+    };
+    for (int b = 0; b < 2; ++b) {
+        if (cudaMallocHost(&stage[b], stage_bytes) != cudaSuccess ||
+            cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming) != cudaSuccess) {
+            cleanup();
+            set_error("upload_ftr: pinned staging allocation failed");
+            return XRB_ERR_CUDA;
+        }
+    }
+    FtrReader r;
+    if ((rc = r.open(path))) {
+        cleanup();
+        return rc;
+    }
+    std::string name;
+    for (int i = 0; i < n_images && rc == XRB_OK; ++i) {
+        const int b = i & 1;
+        int32_t np = 0;
+        if (i >= 2 && cudaEventSynchronize(done[b]) != cudaSuccess) rc = XRB_ERR_CUDA;
+        if (rc == XRB_OK) rc = r.header(&name, &np);
+        if (rc == XRB_OK && np != off[i + 1] - off[i]) {
+            set_error("%s changed while it was being read", path);
+            rc = XRB_ERR_INVALID;
+        }
+        if (rc == XRB_OK) rc = r.keypoints(nullptr);
+        if (rc == XRB_OK) rc = r.descriptors(np ? stage[b] : nullptr);
+        if (rc == XRB_OK && np &&
+            (cudaMemcpyAsync(m->images.as<uint8_t>() + off[i] * kDim, stage[b], (size_t)np * kDim, cudaMemcpyHostToDevice,
+                             m->stream) != cudaSuccess ||
+             cudaEventRecord(done[b], m->stream) != cudaSuccess)) {
+            set_error("upload_ftr: host-to-device copy failed");
+            rc = XRB_ERR_CUDA;
+        }
+    }
+    cudaStreamSynchronize(m->stream);
+    cleanup();
+    if (rc) return rc;
+    m->block = m->images.as<uint8_t>();
+    return set_offsets(m, n_images, off.data());
 }
 
 int xrb_match_attach_device(xrb_matcher *m, int n_images, const int64_t *row_offsets_host,

@@ -117,6 +117,11 @@ class SiftMatchGPU:
                                                 blk.ctypes.data)
         _lib.check(rc, "xrb_match_upload_packed")
 
+    def upload_ftr(self, file_name):
+        """Descriptors of the reference's ftr.bin (io_feature.hpp:76-100) straight to HBM."""
+        self._ensure()
+        _lib.check(_lib.lib().xrb_match_upload_ftr(self._h, str(file_name).encode()), "xrb_match_upload_ftr")
+
     def match_pairs(self, pairs, distmax=DISTANCE_TH, ratiomax=MAX_RATIO, mutual_best_match=1,
                     max_match=MAX_MATCH, capacity=None):
         """pairs [P,2] int32 -> (offsets[P+1] int64, matches[total,2] uint32)."""
