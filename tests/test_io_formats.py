@@ -206,3 +206,61 @@ def test_colmap_rejects_inconsistent_models(tmp_path):
         del io_ref.CAM_PARAMS[5]
     with pytest.raises(_lib.XrbError, match="model"):
         io_formats.ReadColMapDataBinary(d)
+
+
+def _scene_to_model(sc):
+    """A synthetic BA scene as the three model files would hold it (frames list their 2-D points
+    in the scene's observation order; a few untracked points are mixed in)."""
+    cameras = [dict(id=100 + k, model=int(sc.intr_model[k]),
+                    params=sc.intr[k, : io_ref.CAM_PARAMS[int(sc.intr_model[k])]].tolist()) for k in range(sc.n_intr)]
+    p2d = [[] for _ in range(sc.n_cams)]
+    obs_of_track = [[] for _ in range(sc.n_pts)]
+    for o in range(sc.n_obs):
+        c, p = int(sc.obs_cam[o]), int(sc.obs_pt[o])
+        if len(p2d[c]) % 5 == 2:
+            p2d[c].append((1.0, 2.0, -1))                      # an untracked keypoint
+        obs_of_track[p].append((c + 50, len(p2d[c])))
+        p2d[c].append((float(sc.obs_uv[o, 0]), float(sc.obs_uv[o, 1]), 1000 + p))
+    frames = [dict(id=c + 50, q_wxyz=[sc.cam_q[c, 3], *sc.cam_q[c, :3]], t=sc.cam_t[c].tolist(),
+                   camera_id=100 + int(sc.cam_intr[c]), name=f"{c}.png", p2d=p2d[c]) for c in range(sc.n_cams)]
+    tracks = [dict(id=1000 + p, xyz=sc.pts[p].tolist(), error=0.0, obs=obs_of_track[p]) for p in range(sc.n_pts)]
+    return cameras, frames, tracks
+
+
+def test_model_files_feed_the_same_bundle_adjustment(tmp_path):
+    """scene -> cameras/images/points3D.bin -> flat problem -> CPU oracle: same costs, same solution
+    as the scene itself (the observation order differs; the problem must not)."""
+    from tests import oracle_lib as ol
+    from xrsfm_b200 import ba, synth
+    sc = synth.make_scene("C1", scale=0.25)
+    d = str(tmp_path) + "/"
+    io_ref.write_model(d, *_scene_to_model(sc))
+    pr = io_formats.ReadColMapDataBinary(d)
+    assert (pr.n_cams, pr.n_pts, pr.n_obs, pr.n_intr) == (sc.n_cams, sc.n_pts, sc.n_obs, sc.n_intr)
+    np.testing.assert_array_equal(pr.cam_q, sc.cam_q)
+    np.testing.assert_array_equal(pr.pts, sc.pts)
+    np.testing.assert_array_equal(pr.intr, sc.intr)
+    # same multiset of observations
+    a = np.lexsort((sc.obs_pt, sc.obs_cam))
+    b = np.lexsort((pr.obs_pt, pr.obs_cam))
+    np.testing.assert_array_equal(sc.obs_cam[a], pr.obs_cam[b])
+    np.testing.assert_array_equal(sc.obs_pt[a], pr.obs_pt[b])
+    np.testing.assert_array_equal(sc.obs_uv[a], pr.obs_uv[b])
+    pr["cam_t_fixed"][:] = sc.cam_t_fixed                      # the gauge GBA fixes (ba_solver.cc:611-614)
+    ba.make_problem(pr)                                          # dtypes / contiguity the GPU engine insists on
+    opts = ol.ba_options(**ol.GBA_ACCURATE)
+    assert ol.ba_cost(pr, opts) == pytest.approx(ol.ba_cost(sc, opts), rel=1e-12)
+    s1, s2 = ol.ba_solve(sc, opts), ol.ba_solve(pr, opts)
+    assert s1.termination_type == s2.termination_type and s1.num_lm_iterations == s2.num_lm_iterations
+    assert s2.final_cost == pytest.approx(s1.final_cost, rel=1e-9)
+    np.testing.assert_allclose(pr.cam_t, sc.cam_t, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(pr.pts, sc.pts, rtol=1e-7, atol=1e-9)
+    # and back to files: the updated model re-reads as the optimised state
+    out = str(tmp_path / "out") + "/"
+    os.makedirs(out)
+    io_formats.WriteColMapDataBinary(d, out, pr)
+    again = io_formats.ReadColMapDataBinary(out)
+    np.testing.assert_array_equal(again.cam_q, pr.cam_q)
+    np.testing.assert_array_equal(again.cam_t, pr.cam_t)
+    np.testing.assert_array_equal(again.pts, pr.pts)
+    np.testing.assert_array_equal(again.obs_uv, pr.obs_uv)
