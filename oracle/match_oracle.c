@@ -5,12 +5,17 @@
  * or execute this file; it is the checker used by tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs.
  *
- * PARITY STATUS: "parity unpinned" by the reference itself — openxrlab/xrsfm ships no
- * tests, golden vectors or CPU SIFT matcher.  This oracle is pinned
- * instead against the reference's own CUDA kernels, compiled verbatim from
- * /root/reference/3rdparty/SiftGPU/ProgramCU.cu into oracle/_ref/ and run on the GPU box
- * (tests/test_match_gpu.py::test_reference_kernels_agree), and against an independent
- * numpy int32-matmul restatement (tests/test_match_oracle.py).
+ * PARITY STATUS: openxrlab/xrsfm ships no tests, golden vectors or CPU SIFT matcher
+ * (SURVEY.md §4, §8c), so nothing of the reference's own pins this path.  This oracle is
+ * PINNED AGAINST OUTPUTS OF THE REFERENCE ITSELF RUN HERE: the reference's CUDA kernels,
+ * compiled verbatim from /root/reference/3rdparty/SiftGPU/ProgramCU.cu into oracle/_ref/,
+ *   (a) produced the committed golden vectors tests/golden/match_ref_golden.npz on a B200
+ *       (generator: tests/golden/make_match_golden.py; 8 cases: ragged sizes, loose and
+ *       tight thresholds, no mutual filter, truncation at max_match) — checked without a
+ *       GPU by tests/test_match_oracle.py::test_oracle_equals_reference_kernel_golden;
+ *   (b) are run live next to the oracle and the product on the GPU box
+ *       (tests/test_match_gpu.py::test_reference_kernels_agree);
+ * plus an independent numpy int32-matmul restatement (tests/test_match_oracle.py).
  *
  * What is restated (paths relative to the reference tree):
  *   - MultiplyDescriptor_Kernel   3rdparty/SiftGPU/ProgramCU.cu:1491-1578

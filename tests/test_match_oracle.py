@@ -152,3 +152,26 @@ def test_quantisation_rule():
     q = synth.quantize_descriptors(raw)
     assert q[0, 0] == 255 and q[0, 1:].sum() == 0           # 512*sqrt(1) clamps to 255
     assert (q[1] == round(512 * np.sqrt(1 / 128))).all()     # 45
+
+
+def test_oracle_equals_reference_kernel_golden():
+    """The committed outputs of the reference's own CUDA kernels (tests/golden/match_ref_golden.npz,
+    generated on a B200 by tests/golden/make_match_golden.py from ProgramCU.cu compiled verbatim)
+    pin the CPU oracle without a GPU: match lists and both index maps, 8 cases."""
+    import hashlib
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_match_golden", os.path.join(here, "golden", "make_match_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    gold = np.load(os.path.join(here, "golden", "match_ref_golden.npz"))
+    for k, (seed, n1, n2, dmax, rmax, mbm, mm) in enumerate(mk.CASES):
+        a, b = mk.inputs(seed, n1, n2)
+        sha = np.frombuffer(hashlib.sha1(a.tobytes() + b.tobytes()).digest(), dtype=np.uint8)
+        np.testing.assert_array_equal(sha, gold[f"case{k}_sha1"], err_msg=f"case {k}: the synthetic inputs changed")
+        m, m12, m21 = ol.match_pair(a, b, dmax, rmax, mbm, mm, want_m=True)
+        np.testing.assert_array_equal(m, gold[f"case{k}_matches"], err_msg=f"case {k}")
+        np.testing.assert_array_equal(m12, gold[f"case{k}_m12"], err_msg=f"case {k} m12")
+        if mbm:  # the reference only runs the column pass for the mutual test (SiftMatchCU.cpp:190-197)
+            np.testing.assert_array_equal(m21, gold[f"case{k}_m21"], err_msg=f"case {k} m21")
