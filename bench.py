@@ -253,8 +253,8 @@ def run_ba(args, rank, world, local_rank):
                    "n_cams": sc.n_cams, "n_pts": sc.n_pts, "n_obs": sc.n_obs, "scale": args.scale,
                    "parallelism": f"points sharded over {world} GPU(s), cameras replicated, "
                                   "SUM all-reduce of the reduced camera system per solve",
-                   "l2_note": "per-iteration working set (obs 48 MB + S 72 MB + points) exceeds no cache flush: "
-                              "inputs+S > L2 (126 MB) at C2",
+                   "l2_note": "no explicit L2 flush: every iteration streams a working set larger than the 126 MB L2 "
+                              "(observations 48 MB + per-observation records 288 MB + reduced system 72 MB + points)",
                    "iterations_to_convergence": conv.num_lm_iterations,
                    "termination": ba.TERMINATION.get(conv.termination_type),
                    "final_rms_px": float(np.sqrt(conv.final_cost / max(1, conv.num_residuals_reduced))),
