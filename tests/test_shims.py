@@ -15,3 +15,4 @@ def test_shims_compile_link_and_run(tmp_path):
     subprocess.check_call(cmd)
     out = subprocess.check_output([str(exe)], text=True)
     assert "flatten: 0 cams" in out and "VerifyContextGL=" in out
+    assert "ftr roundtrip: ok" in out
