@@ -1,3 +1,4 @@
+#include <vector>
 // Compile + link check of the drop-in shims against mock reference types.
 #include <cstdio>
 #include "xrsfm_mock.h"
@@ -14,7 +15,30 @@ int main() {
     mock::Map map;
     xrsfm_b200::FlatBA f = xrsfm_b200::Flatten(map, false, false);
     std::printf("flatten: %zu cams\n", f.frame_of_cam.size());
+    {   // the LBA window as a flat problem (ba_solver.cc:358-391, 523-584), host logic only
+        mock::Map m2;
+        m2.cameras_[0].params_ = {700.0, 300.0, 200.0, 0.0};
+        m2.frames_.resize(4);
+        m2.tracks_.resize(3);
+        m2.tracks_[1].angle_ = 7.0;                       // well-conditioned point: constant in LBA
+        m2.tracks_[0].observations_[3] = 0, m2.tracks_[1].observations_[3] = 1;  // the new frame (3) sees tracks 0, 1
+        for (int i = 0; i < 4; ++i) {
+            auto &fr = m2.frames_[i];
+            fr.id = i, fr.registered = true;
+            fr.points = {{{1.0, 2.0}}, {{3.0, 4.0}}, {{5.0, 6.0}}};
+            fr.track_ids_ = {0, 1, i == 0 ? -1 : 2};
+        }
+        m2.init_id1 = 0, m2.init_id2 = 9;                 // only one gauge frame inside the window
+        xrsfm_b200::FlatBA lf = xrsfm_b200::FlattenLBA(m2, 3, std::vector<int>{1, 3}, std::vector<int>{0, 3, 2});
+        std::printf("lba: cams=%zu obs=%zu pts=%zu fixed_t=%d%d%d%d fixed_pts=%d%d%d\n", lf.frame_of_cam.size(),
+                    lf.obs_cam.size(), lf.track_of_pt.size(), lf.cam_t_fixed[0], lf.cam_t_fixed[1], lf.cam_t_fixed[2],
+                    lf.cam_t_fixed[3], lf.pt_fixed[0], lf.pt_fixed[1], lf.pt_fixed[2]);
+        m2.init_id1 = 8;                                  // no gauge frame inside: last two of ids2 (3, 2)
+        lf = xrsfm_b200::FlattenLBA(m2, 3, std::vector<int>{1, 3}, std::vector<int>{0, 3, 2});
+        std::printf("lba2: fixed_t=%d%d%d%d\n", lf.cam_t_fixed[0], lf.cam_t_fixed[1], lf.cam_t_fixed[2], lf.cam_t_fixed[3]);
+    }
     if (false) {  // instantiate, never run without a GPU
+        xrsfm_b200::LBA_Solve(map, 0, std::vector<int>{}, std::vector<int>{});
         xrsfm_b200::GBA(map, true, false);
         xrsfm_b200::KGBA_Solve(map);
         uint32_t buf[4][2];

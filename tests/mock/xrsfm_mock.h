@@ -13,7 +13,7 @@ struct Coeffs { double v[4]; double *data() { return v; } const double *data() c
 struct Quat { Coeffs c; Coeffs &coeffs() { return c; } const Coeffs &coeffs() const { return c; } };
 struct Pose { Quat q; Vec3 t; };
 struct CameraT { int model_id_ = 2; std::vector<double> params_; };
-struct Track { Vec3 point3d_; bool outlier = false; };
+struct Track { Vec3 point3d_; bool outlier = false; double angle_ = 0; std::map<int, int> observations_; };
 struct Frame {
     int id = 0, camera_id = 0;
     bool registered = false, is_keyframe = false;

@@ -16,3 +16,7 @@ def test_shims_compile_link_and_run(tmp_path):
     out = subprocess.check_output([str(exe)], text=True)
     assert "flatten: 0 cams" in out and "VerifyContextGL=" in out
     assert "ftr roundtrip: ok" in out
+    # LBA window: frames 0..3 (set order), 11 observations, gauge frame 0 fixed; point 0 free (seen by the
+    # new frame, small angle), point 1 constant (angle > 5), point 2 constant (not seen by the new frame)
+    assert "lba: cams=4 obs=11 pts=3 fixed_t=1000 fixed_pts=011" in out
+    assert "lba2: fixed_t=0011" in out

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cmath>
 #include <unordered_map>
+#include <set>
 #include <vector>
 
 #include "xrsfm_b200.h"
@@ -157,6 +158,93 @@ int KGBA_Solve(MapT &map) {
     }
     Scatter(f, map);
     PrintSolverSummary(s);
+    return rc;
+}
+
+// Flat problem of BASolver::LBA (ba_solver.cc:523-584 with SetUpLBA :358-391) for the window the
+// caller selected: local_frame_ids1 = CovisibilityNeibors(frame_id, map), local_frame_ids2 =
+// FindLocalBundle(frame_id, map) (both stay on the reference side).  Frames are visited in the
+// order of the std::set the reference builds; a point is constant when track.angle_ > 5 or the
+// new frame does not observe it (:380-382); translations: the gauge frames if they are in the
+// window, else the last two of ids2, else the last two of ids1, else the new frame (:552-584).
+template <class MapT>
+FlatBA FlattenLBA(MapT &map, int frame_id, const std::vector<int> &local_frame_ids1,
+                  const std::vector<int> &local_frame_ids2) {
+    std::set<int> local(local_frame_ids1.begin(), local_frame_ids1.end());
+    local.insert(local_frame_ids2.begin(), local_frame_ids2.end());
+    std::set<int> fixed_t;
+    if (local.count(map.init_id1)) fixed_t.insert(map.init_id1);
+    if (local.count(map.init_id2)) fixed_t.insert(map.init_id2);
+    if (fixed_t.empty()) {
+        const std::vector<int> *src = local_frame_ids2.size() >= 2 ? &local_frame_ids2
+                                      : local_frame_ids1.size() >= 2 ? &local_frame_ids1 : nullptr;
+        if (src) {
+            fixed_t.insert((*src)[src->size() - 1]), fixed_t.insert((*src)[src->size() - 2]);
+        } else {
+            std::printf("!!!LBA only one frame\n");
+            fixed_t.insert(frame_id);
+        }
+    }
+    FlatBA f;
+    std::unordered_map<int, int> intr_of_camera, pt_of_track;
+    for (const int id : local) {
+        auto &frame = map.frames_.at(id);
+        int n_mea = 0;
+        for (size_t i = 0; i < frame.track_ids_.size(); ++i) n_mea += frame.track_ids_[i] != -1;
+        if (n_mea == 0) {
+            std::fprintf(stderr, "LBA: NO Measurement In Frame %d\n", frame.id);  // ba_solver.cc:384-385
+            continue;
+        }
+        const int cam = (int)f.frame_of_cam.size();
+        f.frame_of_cam.push_back(frame.id);
+        const double *q = frame.Tcw.q.coeffs().data(), *t = frame.Tcw.t.data();
+        f.cam_q.insert(f.cam_q.end(), q, q + 4);
+        f.cam_t.insert(f.cam_t.end(), t, t + 3);
+        auto it = intr_of_camera.find(frame.camera_id);
+        if (it == intr_of_camera.end()) {
+            auto &camera = map.Camera(frame.camera_id);
+            it = intr_of_camera.emplace(frame.camera_id, (int)f.intr_model.size()).first;
+            f.intr_model.push_back(camera.model_id_);
+            for (int k = 0; k < 8; ++k) f.intr.push_back(k < (int)camera.params_.size() ? camera.params_[k] : 0.0);
+        }
+        f.cam_intr.push_back(it->second);
+        f.cam_q_fixed.push_back(0);
+        f.cam_t_fixed.push_back(fixed_t.count(frame.id) ? 1 : 0);
+        for (size_t i = 0; i < frame.track_ids_.size(); ++i) {
+            const int tid = frame.track_ids_[i];
+            if (tid == -1) continue;
+            auto pit = pt_of_track.find(tid);
+            if (pit == pt_of_track.end()) {
+                pit = pt_of_track.emplace(tid, (int)f.track_of_pt.size()).first;
+                f.track_of_pt.push_back(tid);
+                auto &track = map.tracks_[tid];
+                const double *X = track.point3d_.data();
+                f.pts.insert(f.pts.end(), X, X + 3);
+                f.pt_fixed.push_back((track.angle_ > 5 || track.observations_.count(frame_id) == 0) ? 1 : 0);
+            }
+            f.obs_cam.push_back(cam), f.obs_pt.push_back(pit->second);
+            f.obs_uv.push_back(frame.points[i](0)), f.obs_uv.push_back(frame.points[i](1));
+        }
+    }
+    return f;
+}
+
+// Solver part of BASolver::LBA (ba_solver.cc:586-591): 5 iterations, 1e-4 / 1e-5, no summary print.
+template <class MapT>
+int LBA_Solve(MapT &map, int frame_id, const std::vector<int> &local_frame_ids1,
+              const std::vector<int> &local_frame_ids2) {
+    FlatBA f = FlattenLBA(map, frame_id, local_frame_ids1, local_frame_ids2);
+    xrb_ba_options o;
+    xrb_ba_default_options(&o);
+    o.max_iterations = 5, o.function_tolerance = 1e-4, o.parameter_tolerance = 1e-5;
+    xrb_ba_problem p = f.problem();
+    xrb_ba_summary s;
+    const int rc = xrb_ba_solve(Engine(), &p, &o, &s);
+    if (rc != XRB_OK) {
+        std::fprintf(stderr, "xrb_ba_solve failed (%d): %s\n", rc, xrb_last_error());
+        return rc;
+    }
+    Scatter(f, map);
     return rc;
 }
 
