@@ -903,4 +903,106 @@ double xro_ba_cost(const xrb_ba_problem *P, const xrb_ba_options *opt) {
     }
     return total;
 }
+/* Post-BA filtering (groundwork: no product kernel yet) — restatement of
+ * Point3dProcessor::FilterPoints3d / FilterPoint3d / UpdateTrackAngle
+ * (src/geometry/track_processor.cc:253-349; Reprojection_Error :19-26; CalculateTriangulationAngle
+ * src/geometry/colmap/base/triangulation.cc:124-147; Pose::center src/base/types.h:45) over the
+ * same flat problem the BA takes.  A track's observations are visited in ascending camera index
+ * (the reference iterates a std::map keyed by frame id: flatten frames in id order).
+ *   keep_obs[n_obs]   0 where the observation is deleted (re > max_re or depth outside [1e-3, 1e3],
+ *                     or the whole track became an outlier)
+ *   pt_outlier[n_pts] 1 = SetTrackOutlier; pt_error = mean reprojection error of the kept
+ *                     observations (only written when the track survives the first test);
+ *                     pt_angle = track.angle_ as the early-exit scan leaves it
+ *   counts[2]         num_filtered1 (observations), num_filtered2 (tracks by angle)
+ * Points without observations are left alone (the reference never holds such tracks). */
+int xro_filter_points3d(const xrb_ba_problem *P, double max_re, double deg, uint8_t *keep_obs, uint8_t *pt_outlier,
+                        double *pt_error, double *pt_angle, int32_t *counts) {
+    const double min_tri_angle_rad = deg * 0.0174532925199432954743716805978692718781530857086181640625;
+    std::vector<std::vector<int>> obs_of(P->n_pts);
+    for (int o = 0; o < P->n_obs; ++o) obs_of[P->obs_pt[o]].push_back(o);
+    counts[0] = counts[1] = 0;
+    for (int p = 0; p < P->n_pts; ++p) {
+        std::vector<int> &obs = obs_of[p];
+        std::stable_sort(obs.begin(), obs.end(), [&](int a, int b) { return P->obs_cam[a] < P->obs_cam[b]; });
+        pt_outlier[p] = 0;
+        if (obs.empty()) continue;
+        const double *X = P->pts + 3 * (size_t)p;
+        double re_sum = 0.0;
+        std::vector<int> del;
+        for (const int o : obs) {
+            const int c = P->obs_cam[o];
+            const double *q = P->cam_q + 4 * (size_t)c, *t = P->cam_t + 3 * (size_t)c;
+            const double ux = q[0], uy = q[1], uz = q[2], w = q[3];
+            const double cx_ = 2 * (uy * X[2] - uz * X[1]), cy_ = 2 * (uz * X[0] - ux * X[2]), cz_ = 2 * (ux * X[1] - uy * X[0]);
+            const double pcx = X[0] + w * cx_ + (uy * cz_ - uz * cy_) + t[0];
+            const double pcy = X[1] + w * cy_ + (uz * cx_ - ux * cz_) + t[1];
+            const double pcz = X[2] + w * cz_ + (ux * cy_ - uy * cx_) + t[2];
+            double uv[2], D[4];
+            world_to_image(P->intr_model[P->cam_intr[c]], P->intr + 8 * (size_t)P->cam_intr[c], pcx / pcz, pcy / pcz, uv, D);
+            const double dx = uv[0] - P->obs_uv[2 * (size_t)o], dy = uv[1] - P->obs_uv[2 * (size_t)o + 1];
+            const double re = std::sqrt(dx * dx + dy * dy);
+            keep_obs[o] = 1;
+            if (re > max_re || pcz < 1e-3 || pcz > 1e3)
+                del.push_back(o);
+            else
+                re_sum += re;
+        }
+        if (del.size() >= obs.size() - 1) {  // track_processor.cc:300-303
+            counts[0] += (int32_t)obs.size();
+            pt_outlier[p] = 1;
+            for (const int o : obs) keep_obs[o] = 0;
+            continue;
+        }
+        counts[0] += (int32_t)del.size();
+        for (const int o : del) keep_obs[o] = 0;
+        const size_t n_keep = obs.size() - del.size();
+        pt_error[p] = re_sum / (double)n_keep;
+        // UpdateTrackAngle (:253-277): centres of the remaining observations, pairs (i, j > i) in order,
+        // early exit at the first running maximum above the threshold
+        std::vector<double> ctr;
+        for (const int o : obs) {
+            if (!keep_obs[o]) continue;
+            const int c = P->obs_cam[o];
+            const double *q = P->cam_q + 4 * (size_t)c, *t = P->cam_t + 3 * (size_t)c;
+            // -(q^-1 * t): Eigen's inverse() = conjugate / squaredNorm
+            const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+            const double ux = -q[0] / n2, uy = -q[1] / n2, uz = -q[2] / n2, w = q[3] / n2;
+            const double cx_ = 2 * (uy * t[2] - uz * t[1]), cy_ = 2 * (uz * t[0] - ux * t[2]), cz_ = 2 * (ux * t[1] - uy * t[0]);
+            ctr.push_back(-(t[0] + w * cx_ + (uy * cz_ - uz * cy_)));
+            ctr.push_back(-(t[1] + w * cy_ + (uz * cx_ - ux * cz_)));
+            ctr.push_back(-(t[2] + w * cz_ + (ux * cy_ - uy * cx_)));
+        }
+        const int nc = (int)(ctr.size() / 3);
+        double max_angle = 0;
+        bool done = false;
+        for (int i = 0; i < nc && !done; ++i)
+            for (int j = i + 1; j < nc; ++j) {
+                const double *a = &ctr[3 * i], *b = &ctr[3 * j];
+                const double base2 = (a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]);
+                const double r1 = (X[0] - a[0]) * (X[0] - a[0]) + (X[1] - a[1]) * (X[1] - a[1]) + (X[2] - a[2]) * (X[2] - a[2]);
+                const double r2 = (X[0] - b[0]) * (X[0] - b[0]) + (X[1] - b[1]) * (X[1] - b[1]) + (X[2] - b[2]) * (X[2] - b[2]);
+                const double den = 2.0 * std::sqrt(r1 * r2);
+                double angle = 0.0;
+                if (den != 0.0) {
+                    const double ang = std::fabs(std::acos((r1 + r2 - base2) / den));
+                    angle = std::min(ang, M_PI - ang);
+                }
+                if (angle > max_angle) {
+                    max_angle = angle;
+                    if (max_angle > min_tri_angle_rad) {
+                        done = true;
+                        break;
+                    }
+                }
+            }
+        pt_angle[p] = max_angle;
+        if (max_angle < min_tri_angle_rad) {  // :343-346
+            pt_outlier[p] = 1;
+            counts[1] += 1;
+            for (const int o : obs) keep_obs[o] = 0;
+        }
+    }
+    return 0;
+}
 }
