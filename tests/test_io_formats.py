@@ -264,3 +264,44 @@ def test_model_files_feed_the_same_bundle_adjustment(tmp_path):
     np.testing.assert_array_equal(again.cam_t, pr.cam_t)
     np.testing.assert_array_equal(again.pts, pr.pts)
     np.testing.assert_array_equal(again.obs_uv, pr.obs_uv)
+
+
+def test_random_roundtrips(tmp_path):
+    """Randomised write -> read round trips of both match-side formats (sizes, empty frames,
+    names with spaces, empty pairs)."""
+    rng = np.random.default_rng(99)
+    for it in range(25):
+        n = int(rng.integers(0, 6))
+        counts = rng.integers(0, 40, n)
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        descs = rng.integers(0, 256, (int(off[-1]), 128), dtype=np.uint8)
+        kps = rng.random((int(off[-1]), 4), dtype=np.float32)
+        names = ["".join(rng.choice(list("ab /._-0"), int(rng.integers(0, 12)))) for _ in range(n)]
+        path = str(tmp_path / f"f{it}.bin")
+        io_formats.SaveFeatures(path, names, off, descs, kps)
+        got = io_formats.ReadFeatures(path)
+        assert got["names"] == names
+        np.testing.assert_array_equal(got["row_offsets"], off)
+        np.testing.assert_array_equal(got["descs"], descs)
+        np.testing.assert_array_equal(got["keypoints"], kps)
+
+        P = int(rng.integers(0, 7))
+        ids = np.array([[i, i + 1 + int(rng.integers(0, 3))] for i in range(P)], dtype=np.int32).reshape(P, 2)
+        mcount = rng.integers(0, 30, P)
+        moff = np.concatenate([[0], np.cumsum(mcount)]).astype(np.int64)
+        T = int(moff[-1])
+        mm = rng.integers(0, 5000, (T, 2)).astype(np.uint32)
+        dist = rng.random(T)
+        E = rng.random((P, 9))
+        mask = rng.integers(0, 2, T).astype(np.int8)
+        inl = np.array([mask[moff[k]: moff[k + 1]].sum() for k in range(P)], dtype=np.int32)
+        path = str(tmp_path / f"p{it}.bin")
+        io_formats.SaveFramePairs(path, ids, moff, mm, dist, E, inl, mask)
+        back = io_formats.ReadFramePairs(path)
+        np.testing.assert_array_equal(back["ids"], ids)
+        np.testing.assert_array_equal(back["offsets"], moff)
+        np.testing.assert_array_equal(back["matches"], mm.view(np.int32))
+        np.testing.assert_array_equal(back["distances"], dist)
+        np.testing.assert_array_equal(back["E"], E)
+        np.testing.assert_array_equal(back["inlier_num"], inl)
+        np.testing.assert_array_equal(back["inlier_mask"], mask)
