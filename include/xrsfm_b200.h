@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define XRB_ABI_VERSION 1
+#define XRB_ABI_VERSION 2
 
 typedef enum xrb_status {
     XRB_OK = 0,
@@ -199,13 +199,30 @@ void xrb_ba_default_options(xrb_ba_options *opt); /* Ceres defaults + xrsfm cons
 xrb_ba_solver *xrb_ba_create(int device);
 void xrb_ba_destroy(xrb_ba_solver *s);
 
-/* Multi-GPU exchange hook.  With world > 1 each rank owns a shard of the points (all
- * their observations) and a full replica of the cameras; once per linear solve the
- * solver calls `allreduce(buf_dev, count, user)` — an in-place SUM over ranks of
- * `count` doubles in DEVICE memory, enqueued on `stream` of xrb_ba_solve — on the packed
- * [reduced camera system | rhs | column norms | scalars] buffer.  Typical hook:
- * ncclAllReduce(ncclDouble, ncclSum) or torch.distributed.all_reduce.  Must return 0. */
-typedef int (*xrb_allreduce_fn)(void *buf_dev, size_t count, void *user);
+/* Multi-GPU.  With world > 1 each rank owns a shard of the points (all their observations) and
+ * a full replica of the cameras; once per linear solve the packed
+ * [reduced camera system | rhs | camera blocks | gradient | scalars] buffer is summed over ranks
+ * ("ncclAllReduce(ncclDouble, ncclSum) of the camera-block contributions").
+ *
+ * Native exchange: the library owns an NCCL communicator and issues ncclAllReduce on the
+ * solver's own stream — no host synchronisation, nothing of the caller's in the loop; the
+ * solved points come back through one grouped ncclBroadcast (an all-gather of unequal shards).
+ *   rank 0:     xrb_nccl_unique_id(id)  -> ship the 128 bytes to every rank by any means
+ *   every rank: xrb_ba_comm_init(s, id, rank, world)      (collective: ncclCommInitRank)
+ * NCCL is bound at run time (libnccl.so.2, the copy already mapped in the process if any);
+ * XRB_ERR_COMM when it is missing. */
+#define XRB_NCCL_ID_BYTES 128
+int xrb_nccl_unique_id(uint8_t id[XRB_NCCL_ID_BYTES]);
+int xrb_ba_comm_init(xrb_ba_solver *s, const uint8_t id[XRB_NCCL_ID_BYTES], int rank, int world);
+
+/* Alternative: a caller-supplied hook (used where the caller already owns a communicator).
+ * `allreduce(buf_dev, count, stream, user)` must perform an in-place SUM over ranks of `count`
+ * doubles in DEVICE memory ORDERED ON `stream` (a cudaStream_t): it may return as soon as the
+ * reduction is enqueued there — e.g. ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, comm,
+ * stream) — and the solver launches its next kernel on the same stream without synchronising.
+ * A hook that reduces on another stream must make `stream` wait for it (event) before it
+ * returns.  Must return 0.  A communicator set by xrb_ba_comm_init takes precedence. */
+typedef int (*xrb_allreduce_fn)(void *buf_dev, size_t count, void *stream, void *user);
 int xrb_ba_set_exchange(xrb_ba_solver *s, int rank, int world, xrb_allreduce_fn fn,
                         void *user);
 
@@ -241,11 +258,17 @@ int xrb_ba_residuals(xrb_ba_solver *s, double *out_residuals);
  * [5] whole run; and launches of each (same indices). */
 int xrb_ba_profile(const xrb_ba_solver *s, double ms[6], int64_t launches[6]);
 
-/* Debug hook (no reference counterpart): timeline of the Cholesky kernels of the next solves.
- * enable != 0 arms the recorder; enable == 0 stops it and copies up to cap_records records of
- * 12 int64 words {kernel id, step, t_begin ns, t_end ns, 8 phase cycle counts}; returns the
- * number of records (or a negative status). */
+/* Debug hooks (no reference counterpart).
+ * xrb_debug_chol_trace: enable != 0 arms a recorder in the factorisation's chain CTA; enable == 0
+ * stops it and copies, for the last factorisation, the SM clock after each 64-column block column
+ * (up to cap values); returns the number copied (or a negative status).
+ * xrb_debug_tile_solve: solve A x = rhs for a symmetric positive definite A given dense (n x n
+ * row-major, lower triangle read, entries further than bw from the diagonal ignored) with the
+ * reduced-camera-system solver (tile Cholesky + substitutions) on the current device; the best
+ * device time of `reps` runs goes to *ms_out.  HOST pointers. */
 int xrb_debug_chol_trace(int enable, int64_t *out, int cap_records);
+int xrb_debug_tile_solve(int n, int bw, const double *A, const double *rhs, double *x_out, int reps,
+                         double *ms_out);
 
 /* Finer split of the last run, out[n >= 8]: [0..2] total ms of k_lin (+ memsets), k_gather,
  * k_cam_blocks; [3] linear solves executed; [4] off-diagonal 6x6 blocks of the reduced camera

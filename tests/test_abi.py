@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(h, name), f"{name} declared in include/xrsfm_b200.h but not exported"
     assert set(declared) == set(_lib.SIGNATURES), "ctypes table drifted from the header"
-    assert _lib.lib().xrb_abi_version() == 1
+    assert _lib.lib().xrb_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_gpu():

@@ -263,18 +263,3 @@ def test_degenerate_structure(solver):
     sc4["n_obs"] = 0
     s4 = solver.solve_scene(sc4, **ol.GBA_FAST)
     assert s4.termination_type == 0 and s4.num_residuals_reduced == 0
-
-
-def test_generation1_schur_kernel_still_agrees(monkeypatch):
-    """XRB_BA_SCHUR=1 selects the atomics-based k_schur: same results as the gather pipeline."""
-    monkeypatch.setenv("XRB_BA_SCHUR", "1")
-    s1 = ba.BASolver()
-    sc = synth.make_scene("C1")
-    a = sc.copy_state()
-    r1 = s1.solve_scene(a, **ol.GBA_ACCURATE)
-    monkeypatch.delenv("XRB_BA_SCHUR")
-    b = sc.copy_state()
-    r2 = ba.BASolver().solve_scene(b, **ol.GBA_ACCURATE)
-    assert r1.num_lm_iterations == r2.num_lm_iterations
-    assert r1.final_cost == pytest.approx(r2.final_cost, rel=1e-9)
-    assert np.abs(a.pts - b.pts).max() < 1e-8

@@ -14,7 +14,7 @@ timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 timeout 400 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_ref.json 2>> $OUT/${TAG}_bench.err
 timeout 100 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 100 python tools/chol_trace.py 3 > $OUT/${TAG}_chol_trace.txt 2>&1
+XRB_TRACE=1 timeout 100 python tools/chol_check.py 2994,2993 3000,59 > $OUT/${TAG}_chol_trace.txt 2>&1
 # launch list of one BA run (serialised, cold: compare shares, not absolutes)
 timeout 250 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv \
     --log-file $OUT/${TAG}_ba_launches.csv $B > /dev/null 2>&1

@@ -63,7 +63,7 @@ class ColmapSizes(C.Structure):
                 ("n_p2d", C.c_int64), ("n_obs", C.c_int64)]
 
 
-ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_void_p)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p)
 
 # name -> (restype, argtypes); every symbol include/xrsfm_b200.h declares
 SIGNATURES = {
@@ -89,6 +89,8 @@ SIGNATURES = {
     "xrb_ba_create": (C.c_void_p, [C.c_int]),
     "xrb_ba_destroy": (None, [C.c_void_p]),
     "xrb_ba_set_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p]),
+    "xrb_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "xrb_ba_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "xrb_ba_shard_range": (C.c_int, [C.c_int32, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "xrb_ba_solve": (C.c_int, [C.c_void_p, C.POINTER(BAProblem), C.POINTER(BAOptions),
                                C.POINTER(BASummary)]),
@@ -100,6 +102,7 @@ SIGNATURES = {
     "xrb_ba_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "xrb_ba_profile_detail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "xrb_debug_chol_trace": (C.c_int, [C.c_int, C.c_void_p, C.c_int]),
+    "xrb_debug_tile_solve": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "xrb_ftr_scan": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xrb_ftr_read": (C.c_int, [C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xrb_ftr_write": (C.c_int, [C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

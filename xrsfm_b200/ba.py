@@ -158,14 +158,27 @@ class BASolver:
         keys = ("lin_ms", "gather_ms", "cam_blocks_ms", "solves", "n_blocks", "n_incidences", "nc", "half_bandwidth")
         return dict(zip(keys, list(out)))
 
+    def comm_init(self, rank, world, broadcast_bytes):
+        """Native multi-GPU exchange (xrb_ba_comm_init): the library owns an NCCL communicator and
+        all-reduces on the solver's stream.  `broadcast_bytes(buf: bytearray | None) -> bytes` ships
+        rank 0's 128-byte NCCL id to every rank (any transport: torch.distributed, MPI, a file)."""
+        self._ensure()
+        ident = (C.c_uint8 * 128)()
+        if rank == 0:
+            _lib.check(_lib.lib().xrb_nccl_unique_id(ident), "xrb_nccl_unique_id")
+        raw = broadcast_bytes(bytes(ident) if rank == 0 else None)
+        ident = (C.c_uint8 * 128).from_buffer_copy(raw)
+        _lib.check(_lib.lib().xrb_ba_comm_init(self._h, ident, rank, world), "xrb_ba_comm_init")
+
     def set_exchange(self, rank, world, allreduce):
-        """allreduce(ptr: int, count: int) -> None: in-place SUM over ranks of `count` doubles
-        at device address `ptr` (see include/xrsfm_b200.h xrb_ba_set_exchange)."""
+        """allreduce(ptr: int, count: int, stream: int) -> None: in-place SUM over ranks of `count`
+        doubles at device address `ptr`, ordered on the CUDA stream `stream` (see
+        include/xrsfm_b200.h xrb_ba_set_exchange)."""
         self._ensure()
 
-        def _cb(buf, count, _user):
+        def _cb(buf, count, stream, _user):
             try:
-                allreduce(int(buf), int(count))
+                allreduce(int(buf), int(count), int(stream or 0))
                 return 0
             except Exception as e:  # noqa: BLE001 - surfaced as XRB_ERR_COMM
                 print("exchange hook failed:", e)

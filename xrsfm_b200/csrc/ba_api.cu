@@ -16,13 +16,20 @@
 #include <vector>
 
 #include "ba_structure.cuh"
+#include "nccl_dyn.cuh"
 
 using namespace xrb;
 
 namespace {
 
-struct Ev {
+struct Ev {  // owns its event: every exit path of a run releases it
     cudaEvent_t e = nullptr;
+    Ev() = default;
+    Ev(const Ev &) = delete;
+    Ev &operator=(const Ev &) = delete;
+    ~Ev() {
+        if (e) cudaEventDestroy(e);
+    }
     void rec(cudaStream_t s) {
         if (!e) cudaEventCreate(&e);
         cudaEventRecord(e, s);
@@ -36,33 +43,38 @@ struct xrb_ba_solver {
     int rank = 0, world = 1;
     xrb_allreduce_fn fn = nullptr;
     void *user = nullptr;
-    cudaStream_t own_stream = nullptr;
+    NcclApi::Comm comm = nullptr;  // native exchange (xrb_ba_comm_init); takes precedence over fn
+    std::vector<int32_t> shard_lo;  // [world + 1] point ranges of every rank (multi-GPU)
+    cudaStream_t own_stream = nullptr, side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     bool loaded = false;
     int C = 0, P_total = 0, O_total = 0, n_intr = 0;
     int P_local = 0, O_local = 0, p_lo = 0;
-    int nc = 0, ld = 0, bw = 0;
+    int nc = 0, bw = 0;
+    TileGeom tg;
     int n_var_q = 0, n_var_t = 0, n_var_pts = 0, n_res_blocks = 0;
 
     // device: problem
     DevBuf d_intr, d_intr_model, d_cam_intr, d_colq, d_colt, d_pt_ptr, d_obs_cam, d_obs_uv,
         d_pt_var, d_obs_orig;
-    // generation-2 Schur structure (ba_struct.cu) and per-observation records
+    // Schur structure (ba_struct.cu) and per-observation records
     DevBuf d_obs_pt, d_cam_ptr, d_cam_obs, d_inc, d_blk_ptr, d_blk_cams, d_Tt, d_h;
     BAStructScratch W;  // ba_load.cu / ba_struct.cu working set, kept between loads
-    int schur_gen = 2, n_blocks = 0;
+    int n_blocks = 0;
     int64_t n_inc = 0;
     // device: states
     DevBuf d_q[3], d_t[3], d_X[3];  // 0 = current, 1 = candidate, 2 = initial copy
     int cur = 0;
-    // device: linear system.  E = [S | U | gc | n2c | scalE(8) | slots(world)]
+    // device: linear system.  E = [S tiles | rhs | U | Ud | gc | scalE(8) | slots(world) | n2c]: everything
+    // one linear solve exchanges is one contiguous prefix (n2c travels once, at iteration 0)
     DevBuf d_E, d_Vinv, d_gp, d_sc, d_sp, d_linv, d_yc, d_step_p, d_scal, d_full;
-    size_t off_U = 0, off_gc = 0, off_n2c = 0, off_scalE = 0, off_slots = 0, E_count = 0;
+    size_t off_rhs = 0, off_U = 0, off_Ud = 0, off_gc = 0, off_n2c = 0, off_scalE = 0, off_slots = 0, E_count = 0;
     double *h_scal = nullptr;  // pinned mirror: [scalE(8) | slots(world) | scal2(8) | scalL(8)]
 
     double ms[6] = {0, 0, 0, 0, 0, 0};
     int64_t launches[6] = {0, 0, 0, 0, 0, 0};
-    double ms_kernel[3] = {0, 0, 0};  // generation-2 Schur split: k_lin, k_gather, k_cam_blocks
+    double ms_kernel[3] = {0, 0, 0};  // Schur split: k_lin, k_gather, k_cam_blocks
     int64_t n_steps = 0;              // compute_step calls of the last run
 
     BAProblemDev prob() const {
@@ -74,7 +86,7 @@ struct xrb_ba_solver {
         p.pt_ptr = d_pt_ptr.as<int32_t>(), p.obs_cam = d_obs_cam.as<int32_t>();
         p.obs_uv = d_obs_uv.as<double>(), p.pt_var = d_pt_var.as<uint8_t>();
         p.obs_pt = d_obs_pt.as<int32_t>(), p.cam_ptr = d_cam_ptr.as<int32_t>(), p.cam_obs = d_cam_obs.as<int32_t>();
-        p.n_blocks = schur_gen == 2 ? n_blocks : -1;
+        p.n_blocks = n_blocks;
         p.blk_ptr = d_blk_ptr.as<int32_t>(), p.blk_cams = d_blk_cams.as<int2>(), p.inc = d_inc.as<int2>();
         return p;
     }
@@ -82,7 +94,7 @@ struct xrb_ba_solver {
     BALinSys linsys() const {
         BALinSys L;
         double *E = d_E.as<double>();
-        L.S = E, L.ld = ld, L.U = E + off_U, L.gc = E + off_gc, L.n2c = E + off_n2c;
+        L.S = E, L.tg = tg, L.rhs = E + off_rhs, L.U = E + off_U, L.Ud = E + off_Ud, L.gc = E + off_gc, L.n2c = E + off_n2c;
         L.Vinv = d_Vinv.as<double>(), L.gp = d_gp.as<double>();
         L.sc = d_sc.as<double>(), L.sp = d_sp.as<double>();
         L.Tt = d_Tt.as<double>(), L.h = d_h.as<double>();
@@ -93,15 +105,25 @@ struct xrb_ba_solver {
     double *scal2() const { return d_scal.as<double>(); }
     double *scalL() const { return d_scal.as<double>() + SC_COUNT; }
 
+    // In-place SUM over ranks of `count` doubles, ordered on `st`: ncclAllReduce(ncclDouble,
+    // ncclSum) on the solver's own stream — no host synchronisation — or the caller's hook.
     int exchange(double *buf, size_t count, cudaStream_t st) {
         if (world <= 1) return XRB_OK;
+        if (comm) {
+            const NcclApi *nc_ = nccl_api();
+            const int r = nc_->AllReduce(buf, buf, count, NcclApi::kFloat64, NcclApi::kSum, comm, st);
+            if (r != 0) {
+                set_error("ncclAllReduce failed: %s", nc_->GetErrorString(r));
+                return XRB_ERR_COMM;
+            }
+            launches[4]++;
+            return XRB_OK;
+        }
         if (!fn) {
-            set_error("world > 1 but no exchange hook set");
+            set_error("world > 1 but neither xrb_ba_comm_init nor an exchange hook was set");
             return XRB_ERR_COMM;
         }
-        // the hook enqueues on ITS stream; order it after ours and ours after it
-        XRB_CUDA(cudaStreamSynchronize(st));
-        if (fn(buf, count, user) != 0) {
+        if (fn(buf, count, (void *)st, user) != 0) {
             set_error("exchange hook failed");
             return XRB_ERR_COMM;
         }
@@ -164,6 +186,7 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
     s->nc = info.nc, s->n_var_q = info.n_var_q, s->n_var_t = info.n_var_t, s->n_var_pts = info.n_var_pts;
     s->n_res_blocks = info.n_res_blocks, s->bw = info.bw;
     s->p_lo = info.p_lo, s->P_local = info.P_local, s->O_local = info.O_local;
+    s->shard_lo = info.shard_lo;
     lt.lap("structure (device)");
 
     if ((rc = upload(s->d_intr, P->intr, 8 * (size_t)P->n_intr, st))) return rc;
@@ -183,27 +206,24 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
     }
     s->cur = 0;
     lt.lap("state + intrinsics uploads");
-    // ---- generation-2 Schur structure: per-observation records, block incidence lists
+    // ---- Schur structure: per-observation records, block incidence lists
     {
-        const char *env = getenv("XRB_BA_SCHUR");
-        s->schur_gen = (env && atoi(env) == 1) ? 1 : 2;
         s->n_blocks = 0, s->n_inc = 0;
-        if (s->schur_gen == 2) {
-            if ((rc = s->d_Tt.reserve(std::max<size_t>(1, 18 * (size_t)s->O_local) * 8))) return rc;
-            if ((rc = s->d_h.reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
-            BAProblemDev pd = s->prob();
-            if ((rc = ba_build_block_lists(pd, s->W, s->d_inc, s->d_blk_ptr, s->d_blk_cams, &s->n_blocks, &s->n_inc, st)))
-                return rc;
-            lt.lap("block lists (device)");
-        }
+        if ((rc = s->d_Tt.reserve(std::max<size_t>(1, 18 * (size_t)s->O_local) * 8))) return rc;
+        if ((rc = s->d_h.reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
+        BAProblemDev pd = s->prob();
+        if ((rc = ba_build_block_lists(pd, s->W, s->d_inc, s->d_blk_ptr, s->d_blk_cams, &s->n_blocks, &s->n_inc, st)))
+            return rc;
+        lt.lap("block lists (device)");
     }
     // ---- linear-system storage
     const int nc = s->nc;
-    s->ld = ((nc + 1 + 7) / 8) * 8;
-    const size_t nS = (size_t)(nc + 1) * s->ld;
-    s->off_U = nS, s->off_gc = s->off_U + (size_t)nc * 6, s->off_n2c = s->off_gc + nc;
-    s->off_scalE = s->off_n2c + nc, s->off_slots = s->off_scalE + SC_COUNT;
-    s->E_count = s->off_slots + s->world;
+    s->tg = TileGeom::make(nc, s->bw);
+    const size_t nS = (size_t)s->tg.n_tiles() * 4096;
+    s->off_rhs = nS, s->off_U = s->off_rhs + (size_t)s->tg.nt * 64;
+    s->off_Ud = s->off_U + (size_t)nc * 6, s->off_gc = s->off_Ud + (size_t)nc * 6, s->off_scalE = s->off_gc + nc;
+    s->off_slots = s->off_scalE + SC_COUNT, s->off_n2c = s->off_slots + s->world;
+    s->E_count = s->off_n2c + nc;
     if ((rc = s->d_E.reserve(s->E_count * 8))) return rc;
     if ((rc = s->d_Vinv.reserve(std::max<size_t>(1, 6 * (size_t)s->P_local) * 8))) return rc;
     if ((rc = s->d_gp.reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
@@ -211,7 +231,7 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
     if ((rc = s->d_step_p.reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
     if ((rc = s->d_sc.reserve(std::max<size_t>(1, nc) * 8))) return rc;
     if ((rc = s->d_yc.reserve(std::max<size_t>(1, nc) * 8))) return rc;
-    if ((rc = s->d_linv.reserve((size_t)((nc + 63) / 64 + 1) * 64 * 64 * 8))) return rc;
+    if ((rc = s->d_linv.reserve((size_t)(s->tg.nt + 1) * 4 * 256 * 8))) return rc;
     if ((rc = s->d_scal.reserve(2 * SC_COUNT * 8))) return rc;
     if (!s->h_scal) XRB_CUDA(cudaMallocHost(&s->h_scal, (3 * SC_COUNT + 64) * sizeof(double)));
     if (s->world > 64) {
@@ -238,32 +258,30 @@ int compute_step(xrb_ba_solver *s, const BAConsts &k, double radius, cudaStream_
     const double inv_radius = 1.0 / radius;
     int rc;
     ev[0].rec(st);
-    // zero S, U, gc (n2c untouched), scalE + slots, scal2 + scalL
+    // zero S, rhs, U, gc, scalE + slots (n2c untouched), scal2 + scalL
     XRB_CUDA(cudaMemsetAsync(s->d_E.p, 0, s->off_n2c * 8, st));
-    XRB_CUDA(cudaMemsetAsync(s->scalE(), 0, (SC_COUNT + s->world) * 8, st));
     XRB_CUDA(cudaMemsetAsync(s->d_scal.p, 0, 2 * SC_COUNT * 8, st));
-    if (s->schur_gen == 2) {
-        if ((rc = ba_launch_lin(P, x, k, L, inv_radius, s->scalE(), st))) return rc;
-        ev[7].rec(st);
-        if ((rc = ba_launch_gather(P, L, st))) return rc;
-        ev[8].rec(st);
-        if ((rc = ba_launch_cam_blocks(P, x, k, L, st))) return rc;
-        s->launches[0] += 3;
-    } else {
-        if ((rc = ba_launch_schur(P, x, k, L, inv_radius, s->scalE(), st))) return rc;
-        s->launches[0]++;
-    }
+    if ((rc = ba_launch_lin(P, x, k, L, inv_radius, s->scalE(), st))) return rc;
+    ev[7].rec(st);
+    // the camera-major reduction reads the records but never S: it runs beside the gather
+    XRB_CUDA(cudaEventRecord(s->ev_fork, st));
+    XRB_CUDA(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
+    if ((rc = ba_launch_cam_blocks(P, x, k, L, s->side_stream))) return rc;
+    XRB_CUDA(cudaEventRecord(s->ev_join, s->side_stream));
+    if ((rc = ba_launch_gather(P, L, st))) return rc;
+    ev[8].rec(st);
+    XRB_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+    s->launches[0] += 3;
     ev[1].rec(st);
     if (s->world > 1) {
         XRB_CUDA(cudaMemcpyAsync(s->slots() + s->rank, s->scalE() + SC_GRAD_MAX_PT, 8, cudaMemcpyDeviceToDevice, st));
-        // S | U | gc  and the scalar tail travel in two pieces (n2c is skipped)
+        // S | U | gc | scalars | per-rank slots: ONE all-reduce per linear solve
         if ((rc = s->exchange(s->d_E.as<double>(), s->off_n2c, st))) return rc;
-        if ((rc = s->exchange(s->scalE(), SC_COUNT + s->world, st))) return rc;
     }
     ev[2].rec(st);
     if ((rc = ba_launch_cam_diag(P, x, L, inv_radius, s->scalL(), st))) return rc;
-    if ((rc = ba_launch_cholesky_solve(L.S, s->nc, s->ld, s->bw, s->d_linv.as<double>(), s->d_yc.as<double>(),
-                                       s->scalL() + SC_FAIL, st, &s->launches[1])))
+    if ((rc = ba_launch_tile_cholesky_solve(s->tg, L.S, L.rhs, s->d_linv.as<double>(), s->d_yc.as<double>(),
+                                            s->scalL() + SC_FAIL, st, &s->launches[1])))
         return rc;
     s->launches[1]++;
     ev[3].rec(st);
@@ -295,7 +313,7 @@ int compute_step(xrb_ba_solver *s, const BAConsts &k, double radius, cudaStream_
              std::isfinite(out.cand_cost) && std::isfinite(out.step_norm);
     // phase timings
     s->n_steps++;
-    if (s->schur_gen == 2) {
+    {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, ev[0].e, ev[7].e) == cudaSuccess) s->ms_kernel[0] += t;  // memsets + k_lin
         if (cudaEventElapsedTime(&t, ev[7].e, ev[8].e) == cudaSuccess) s->ms_kernel[1] += t;
@@ -392,8 +410,11 @@ int do_run(xrb_ba_solver *s, const xrb_ba_options *O, xrb_ba_summary *sum, cudaS
         xnorm = std::sqrt(n2);
     }
 
+    double min_cost = 0.0;
+    bool have_min = false;
     auto log_iter = [&](const xrb_ba_iteration &it) {
         if (sum->n_iterations_logged < 128) sum->iterations[sum->n_iterations_logged++] = it;
+        if (!have_min || it.cost < min_cost) min_cost = it.cost, have_min = true;
         if (it.step_is_successful) sum->num_successful_steps++; else sum->num_unsuccessful_steps++;
         if (O->verbose && s->rank == 0)
             printf("%4d % .6e % .2e % .2e % .2e % .2e % .2e\n", it.iteration, it.cost, it.cost_change,
@@ -471,8 +492,7 @@ int do_run(xrb_ba_solver *s, const xrb_ba_options *O, xrb_ba_summary *sum, cudaS
         it = cur;
         log_iter(it);
     }
-    sum->final_cost = sum->initial_cost;
-    for (int i = 0; i < sum->n_iterations_logged; ++i) sum->final_cost = std::min(sum->final_cost, sum->iterations[i].cost);
+    sum->final_cost = have_min ? std::min(sum->initial_cost, min_cost) : sum->initial_cost;
     ev_run[1].rec(st);
     XRB_CUDA(cudaStreamSynchronize(st));
     float tr = 0.f;
@@ -481,8 +501,6 @@ int do_run(xrb_ba_solver *s, const xrb_ba_options *O, xrb_ba_summary *sum, cudaS
     sum->linear_solver_seconds = (s->ms[0] + s->ms[1] + s->ms[2]) * 1e-3;
     sum->residual_seconds = s->ms[3] * 1e-3;
     sum->total_time_in_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    for (auto &e : ev) if (e.e) cudaEventDestroy(e.e);
-    for (auto &e : ev_run) if (e.e) cudaEventDestroy(e.e);
     return XRB_OK;
 }
 
@@ -498,14 +516,35 @@ int do_fetch(xrb_ba_solver *s, xrb_ba_problem *P) {
     if (s->world <= 1) {
         if (s->P_local)
             XRB_CUDA(cudaMemcpyAsync(P->pts, s->d_X[s->cur].p, 3 * (size_t)s->P_local * 8, cudaMemcpyDeviceToHost, st));
-    } else {  // every rank returns every point: zero-padded shards summed through the hook
+    } else {  // every rank returns every point
         int rc = s->d_full.reserve(std::max<size_t>(1, 3 * (size_t)s->P_total) * 8);
         if (rc) return rc;
-        XRB_CUDA(cudaMemsetAsync(s->d_full.p, 0, 3 * (size_t)s->P_total * 8, st));
-        if (s->P_local)
-            XRB_CUDA(cudaMemcpyAsync(s->d_full.as<double>() + 3 * (size_t)s->p_lo, s->d_X[s->cur].p,
-                                     3 * (size_t)s->P_local * 8, cudaMemcpyDeviceToDevice, st));
-        if ((rc = s->exchange(s->d_full.as<double>(), 3 * (size_t)s->P_total, st))) return rc;
+        if (s->comm && (int)s->shard_lo.size() == s->world + 1) {
+            // all-gather of unequal shards: one broadcast per owner, grouped into one NCCL operation
+            const NcclApi *nc_ = nccl_api();
+            if (s->P_local)
+                XRB_CUDA(cudaMemcpyAsync(s->d_full.as<double>() + 3 * (size_t)s->p_lo, s->d_X[s->cur].p,
+                                         3 * (size_t)s->P_local * 8, cudaMemcpyDeviceToDevice, st));
+            int r = nc_->GroupStart();
+            for (int o = 0; o < s->world && r == 0; ++o) {
+                const size_t lo = s->shard_lo[o], n = (size_t)s->shard_lo[o + 1] - lo;
+                if (!n) continue;
+                double *seg = s->d_full.as<double>() + 3 * lo;
+                r = nc_->Broadcast(seg, seg, 3 * n, NcclApi::kFloat64, o, s->comm, st);
+            }
+            const int r2 = nc_->GroupEnd();
+            if (r != 0 || r2 != 0) {
+                set_error("ncclBroadcast (shard gather) failed: %s", nc_->GetErrorString(r ? r : r2));
+                return XRB_ERR_COMM;
+            }
+            s->launches[4]++;
+        } else {  // hook: zero-padded shards summed
+            XRB_CUDA(cudaMemsetAsync(s->d_full.p, 0, 3 * (size_t)s->P_total * 8, st));
+            if (s->P_local)
+                XRB_CUDA(cudaMemcpyAsync(s->d_full.as<double>() + 3 * (size_t)s->p_lo, s->d_X[s->cur].p,
+                                         3 * (size_t)s->P_local * 8, cudaMemcpyDeviceToDevice, st));
+            if ((rc = s->exchange(s->d_full.as<double>(), 3 * (size_t)s->P_total, st))) return rc;
+        }
         XRB_CUDA(cudaMemcpyAsync(P->pts, s->d_full.p, 3 * (size_t)s->P_total * 8, cudaMemcpyDeviceToHost, st));
     }
     XRB_CUDA(cudaStreamSynchronize(st));
@@ -556,7 +595,10 @@ xrb_ba_solver *xrb_ba_create(int device) {
     if (select_device(device) != XRB_OK) return nullptr;
     xrb_ba_solver *s = new xrb_ba_solver();
     s->device = device;
-    if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         set_error("cudaStreamCreate failed");
         delete s;
         return nullptr;
@@ -577,7 +619,12 @@ void xrb_ba_destroy(xrb_ba_solver *s) {
     s->W.release();
     for (int i = 0; i < 3; ++i) s->d_q[i].release(), s->d_t[i].release(), s->d_X[i].release();
     if (s->h_scal) cudaFreeHost(s->h_scal);
+    if (s->comm)
+        if (const NcclApi *nc_ = nccl_api()) nc_->CommDestroy(s->comm);
     cudaStreamDestroy(s->own_stream);
+    if (s->side_stream) cudaStreamDestroy(s->side_stream);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     delete s;
 }
 
@@ -588,6 +635,45 @@ int xrb_ba_set_exchange(xrb_ba_solver *s, int rank, int world, xrb_allreduce_fn 
     }
     s->rank = rank, s->world = world, s->fn = fn, s->user = user;
     s->loaded = false;  // sharding changes
+    return XRB_OK;
+}
+
+int xrb_nccl_unique_id(uint8_t id[XRB_NCCL_ID_BYTES]) {
+    static_assert(sizeof(NcclApi::UniqueId) == XRB_NCCL_ID_BYTES, "ncclUniqueId is 128 bytes");
+    const NcclApi *nc_ = nccl_api();
+    if (!nc_ || !id) return nc_ ? XRB_ERR_INVALID : XRB_ERR_COMM;
+    NcclApi::UniqueId u;
+    const int r = nc_->GetUniqueId(&u);
+    if (r != 0) {
+        set_error("ncclGetUniqueId failed: %s", nc_->GetErrorString(r));
+        return XRB_ERR_COMM;
+    }
+    memcpy(id, u.internal, XRB_NCCL_ID_BYTES);
+    return XRB_OK;
+}
+
+int xrb_ba_comm_init(xrb_ba_solver *s, const uint8_t id[XRB_NCCL_ID_BYTES], int rank, int world) {
+    if (!s || !id || world < 1 || rank < 0 || rank >= world || world > 64) {
+        set_error("ba_comm_init: bad rank/world (world <= 64)");
+        return XRB_ERR_INVALID;
+    }
+    XRB_CUDA(cudaSetDevice(s->device));
+    if (s->comm) {
+        if (const NcclApi *nc_ = nccl_api()) nc_->CommDestroy(s->comm);
+        s->comm = nullptr;
+    }
+    s->rank = rank, s->world = world, s->loaded = false;
+    if (world == 1) return XRB_OK;
+    const NcclApi *nc_ = nccl_api();
+    if (!nc_) return XRB_ERR_COMM;
+    NcclApi::UniqueId u;
+    memcpy(u.internal, id, XRB_NCCL_ID_BYTES);
+    const int r = nc_->CommInitRank(&s->comm, world, u, rank);
+    if (r != 0) {
+        s->comm = nullptr;
+        set_error("ncclCommInitRank failed: %s", nc_->GetErrorString(r));
+        return XRB_ERR_COMM;
+    }
     return XRB_OK;
 }
 
@@ -654,7 +740,60 @@ int xrb_ba_residuals(xrb_ba_solver *s, double *out) {
 /* debug hook (not part of the reference surface): timeline of the Cholesky kernels */
 int xrb_debug_chol_trace(int enable, int64_t *out, int cap_records) {
     static_assert(sizeof(long long) == sizeof(int64_t), "");
-    return ba_chol_trace(enable, reinterpret_cast<long long *>(out), cap_records);
+    return ba_tile_cholesky_trace(enable, reinterpret_cast<long long *>(out), cap_records);
+}
+
+/* debug hook (not part of the reference surface): factor + solve one dense-stored SPD system with
+ * the tile solver, on the current device */
+int xrb_debug_tile_solve(int n, int bw, const double *A, const double *rhs, double *x_out, int reps,
+                         double *ms_out) {
+    if (n <= 0 || !A || !rhs || !x_out || reps < 1) return XRB_ERR_INVALID;
+    XRB_CUDA(cudaFree(0));
+    const TileGeom g = TileGeom::make(n, bw);
+    const size_t nS = (size_t)g.n_tiles() * 4096, nR = (size_t)g.nt * 64;
+    std::vector<double> packed(nS + nR, 0.0);
+    for (int r = 0; r < n; ++r)
+        for (int c = std::max(0, r - bw); c <= r; ++c) packed[g.at(r, c)] = A[(size_t)r * n + c];
+    for (int r = 0; r < n; ++r) packed[nS + r] = rhs[r];
+    DevBuf E, dinv, x, fail;
+    int rc;
+    if ((rc = E.reserve(packed.size() * 8)) || (rc = dinv.reserve((size_t)(g.nt + 1) * 1024 * 8)) ||
+        (rc = x.reserve(nR * 8)) || (rc = fail.reserve(8)))
+        return rc;
+    cudaStream_t st;
+    XRB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int it = 0; it < reps && rc == XRB_OK; ++it) {
+        cudaMemcpyAsync(E.p, packed.data(), packed.size() * 8, cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(fail.p, 0, 8, st);
+        cudaMemsetAsync(x.p, 0, nR * 8, st);
+        cudaEventRecord(e0, st);
+        rc = ba_launch_tile_cholesky_solve(g, E.as<double>(), E.as<double>() + nS, dinv.as<double>(), x.as<double>(),
+                                           fail.as<double>(), st, nullptr);
+        cudaEventRecord(e1, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) rc = XRB_ERR_CUDA;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = std::min(best, ms);
+    }
+    double f = 0.0;
+    if (rc == XRB_OK) {
+        cudaMemcpy(x_out, x.p, (size_t)n * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&f, fail.p, 8, cudaMemcpyDeviceToHost);
+        if (f != 0.0) {
+            set_error("tile solve: %s", f == 2.0 ? "a dependency wait gave up (aborted)" : "non-positive pivot");
+            rc = XRB_ERR_NUMERIC;
+        }
+    } else if (rc == XRB_ERR_CUDA) {
+        set_error("tile solve: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (ms_out) *ms_out = best;
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    cudaStreamDestroy(st);
+    E.release(), dinv.release(), x.release(), fail.release();
+    return rc;
 }
 
 int xrb_ba_profile_detail(const xrb_ba_solver *s, double *out, int n) {

@@ -296,210 +296,16 @@ int ba_launch_finish_scaling(const BAProblemDev &P, const BALinSys &L, cudaStrea
 }
 
 // =====================================================================================
-// 2. Fused linearise + Schur complement.  One warp per point, one observation per lane.
-//    Phase A: r, J, Huber; V = sum JX^T JX, g = sum JX^T r by warp shuffles.
-//    Phase B: V + D_p^2 (LM diagonal of the point block) inverted in registers.
-//    Phase C: per observation W = Jc^T JX (6x3), T = W V^-1 staged in shared memory;
-//             U_c += Jc^T Jc, g_c += Jc^T r, rhs_c += Jc^T r - T g  (FP64 atomics).
-//    Phase D: S[c_i,c_j] -= T_i W_j^T for every unordered observation pair of the point,
-//             36 entries per pair spread over the lanes, FP64 atomics into the lower triangle.
-// =====================================================================================
-struct __align__(16) WarpStage {
-    double T[kChunk][18];
-    double W[kChunk][18];
-    int colsA[kChunk][6];
-    int colsB[kChunk][6];
-};
-
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_schur(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L, double inv_radius,
-        double *__restrict__ scalars) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpStage &sm = reinterpret_cast<WarpStage *>(smem_raw)[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int n = P.nc, ld = L.ld;
-    double *rhs = L.S + (size_t)n * ld;
-    double gmax = 0.0;
-
-    for (int p = warp; p < P.n_pts_local; p += nwarps) {
-        const int k0 = P.pt_ptr[p], kn = P.pt_ptr[p + 1] - k0;
-        if (kn == 0) continue;
-        const bool pvar = P.pt_var[p] != 0;
-        const int nchunks = (kn + kChunk - 1) / kChunk;
-        // ---- Phase A
-        double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
-        LinObs lo;  // stays live for the single-chunk case
-        lo.active = false;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int i = ch * kChunk + lane;
-            lo.active = false;
-            if (i < kn) lin_obs(P, x, k, L, k0 + i, p, pvar, lo);
-            if (lo.active) {
-                const double *J = lo.JX;
-                V[0] += J[0] * J[0] + J[3] * J[3], V[1] += J[0] * J[1] + J[3] * J[4];
-                V[2] += J[0] * J[2] + J[3] * J[5], V[3] += J[1] * J[1] + J[4] * J[4];
-                V[4] += J[1] * J[2] + J[4] * J[5], V[5] += J[2] * J[2] + J[5] * J[5];
-                g[0] += J[0] * lo.r0 + J[3] * lo.r1;
-                g[1] += J[1] * lo.r0 + J[4] * lo.r1;
-                g[2] += J[2] * lo.r0 + J[5] * lo.r1;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 6; ++j) V[j] = warp_sum(V[j]);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) g[j] = warp_sum(g[j]);
-        // ---- Phase B: (V + D^2)^-1, D^2 = clamp(diag V, 1e-6, 1e32) / radius
-        double Vi[6] = {0, 0, 0, 0, 0, 0};
-        if (pvar) {
-            const double a = V[0] + fmin(fmax(V[0], 1e-6), 1e32) * inv_radius;
-            const double d = V[3] + fmin(fmax(V[3], 1e-6), 1e32) * inv_radius;
-            const double f = V[5] + fmin(fmax(V[5], 1e-6), 1e32) * inv_radius;
-            const double b = V[1], c = V[2], e = V[4];
-            const double A = d * f - e * e, B = c * e - b * f, Cc = b * e - c * d;
-            const double det = a * A + b * B + c * Cc;
-            const double id = 1.0 / det;
-            Vi[0] = A * id, Vi[1] = B * id, Vi[2] = Cc * id;
-            Vi[3] = (a * f - c * c) * id, Vi[4] = (b * c - a * e) * id, Vi[5] = (a * d - b * b) * id;
-            if (lane == 0) {
-                if (!(fabs(det) > 0.0) || !isfinite(id)) scalars[SC_FAIL] = 1.0;
-#pragma unroll
-                for (int j = 0; j < 6; ++j) L.Vinv[6 * (size_t)p + j] = Vi[j];
-#pragma unroll
-                for (int j = 0; j < 3; ++j) L.gp[3 * (size_t)p + j] = g[j];
-                const double *s = L.sp + 3 * (size_t)p;
-                gmax = fmax(gmax, fmax(fabs(g[0] / s[0]), fmax(fabs(g[1] / s[1]), fabs(g[2] / s[2]))));
-            }
-        }
-        // ---- Phases C + D over chunk pairs (a single pass when kn <= 32)
-        for (int ca = 0; ca < nchunks; ++ca) {
-            const int ia = ca * kChunk + lane;
-            const int na = min(kChunk, kn - ca * kChunk);
-            if (nchunks > 1) {  // re-linearise chunk ca (registers were overwritten)
-                lo.active = false;
-                if (ia < kn) lin_obs(P, x, k, L, k0 + ia, p, pvar, lo);
-            }
-            double Wr[18];
-            __syncwarp();
-            if (ia < kn) {
-#pragma unroll
-                for (int j = 0; j < 6; ++j) sm.colsA[lane][j] = lo.active ? lo.cols[j] : -1;
-            }
-            if (ia < kn && lo.active) {
-#pragma unroll
-                for (int a = 0; a < 6; ++a)
-#pragma unroll
-                    for (int b = 0; b < 3; ++b) Wr[a * 3 + b] = lo.Jc[a] * lo.JX[b] + lo.Jc[6 + a] * lo.JX[3 + b];
-#pragma unroll
-                for (int a = 0; a < 6; ++a) {
-                    const double t0 = Wr[a * 3] * Vi[0] + Wr[a * 3 + 1] * Vi[1] + Wr[a * 3 + 2] * Vi[2];
-                    const double t1 = Wr[a * 3] * Vi[1] + Wr[a * 3 + 1] * Vi[3] + Wr[a * 3 + 2] * Vi[4];
-                    const double t2 = Wr[a * 3] * Vi[2] + Wr[a * 3 + 1] * Vi[4] + Wr[a * 3 + 2] * Vi[5];
-                    sm.T[lane][a * 3] = t0, sm.T[lane][a * 3 + 1] = t1, sm.T[lane][a * 3 + 2] = t2;
-                    const int col = lo.cols[a];
-                    if (col >= 0) {
-                        // camera block-diagonal row (6 wide), gradient and reduced rhs
-#pragma unroll
-                        for (int b = 0; b < 6; ++b)
-                            if (lo.cols[b] >= 0 && b <= a)
-                                atomicAdd(&L.U[(size_t)col * 6 + b], lo.Jc[a] * lo.Jc[b] + lo.Jc[6 + a] * lo.Jc[6 + b]);
-                        const double gr = lo.Jc[a] * lo.r0 + lo.Jc[6 + a] * lo.r1;
-                        atomicAdd(&L.gc[col], gr);
-                        atomicAdd(&rhs[col], gr - (t0 * g[0] + t1 * g[1] + t2 * g[2]));
-                    }
-                }
-            }
-            if (!pvar) continue;  // constant point: no elimination, only the F^T F terms above
-            for (int cb = 0; cb <= ca; ++cb) {
-                const int nb = min(kChunk, kn - cb * kChunk);
-                __syncwarp();
-                if (cb == ca) {
-                    if (ia < kn) {
-#pragma unroll
-                        for (int j = 0; j < 6; ++j) sm.colsB[lane][j] = sm.colsA[lane][j];
-                        if (lo.active) {
-#pragma unroll
-                            for (int j = 0; j < 18; ++j) sm.W[lane][j] = Wr[j];
-                        }
-                    }
-                } else {
-                    const int ib = cb * kChunk + lane;
-                    LinObs lb;
-                    lb.active = false;
-                    if (ib < kn) lin_obs(P, x, k, L, k0 + ib, p, pvar, lb);
-                    if (ib < kn) {
-#pragma unroll
-                        for (int j = 0; j < 6; ++j) sm.colsB[lane][j] = lb.active ? lb.cols[j] : -1;
-                        if (lb.active) {
-#pragma unroll
-                            for (int a = 0; a < 6; ++a)
-#pragma unroll
-                                for (int b = 0; b < 3; ++b)
-                                    sm.W[lane][a * 3 + b] = lb.Jc[a] * lb.JX[b] + lb.Jc[6 + a] * lb.JX[3 + b];
-                        }
-                    }
-                }
-                __syncwarp();
-                // unordered pairs {i in chunk a, j in chunk b}; same chunk: j <= i
-                const int npairs = (cb == ca) ? na * (na + 1) / 2 : na * nb;
-                for (int it = lane; it < npairs * 36; it += 32) {
-                    const int pr = it / 36, e = it - pr * 36;
-                    int i, j;
-                    if (cb == ca) {
-                        i = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
-                        while (i * (i + 1) / 2 > pr) --i;
-                        while ((i + 1) * (i + 2) / 2 <= pr) ++i;
-                        j = pr - i * (i + 1) / 2;
-                    } else {
-                        i = pr / nb, j = pr - i * nb;
-                    }
-                    const int a = e / 6, b = e - a * 6;
-                    const bool same_obs = (cb == ca) && (i == j);
-                    if (same_obs && b > a) continue;  // symmetric block: lower entries once
-                    const int r = sm.colsA[i][a], c = sm.colsB[j][b];
-                    if (r < 0 || c < 0) continue;
-                    double val = sm.T[i][a * 3] * sm.W[j][b * 3] + sm.T[i][a * 3 + 1] * sm.W[j][b * 3 + 1] +
-                                 sm.T[i][a * 3 + 2] * sm.W[j][b * 3 + 2];
-                    // two observations of the same camera: the block is M + M^T, whose
-                    // diagonal is 2 M_aa (the off-diagonal pairs land on the same entry)
-                    if (!same_obs && r == c) val *= 2.0;
-                    const int hi = r >= c ? r : c, lo_ = r >= c ? c : r;
-                    atomicAdd(&L.S[(size_t)hi * ld + lo_], -val);
-                }
-            }
-        }
-    }
-    if (lane == 0 && gmax > 0.0) atomic_max_nonneg(&scalars[SC_GRAD_MAX_PT], gmax);
-}
-
-int ba_launch_schur(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
-                    const BALinSys &L, double inv_radius, double *scalars, cudaStream_t st) {
-    if (P.n_pts_local > 0) {
-        const size_t smem = sizeof(WarpStage) * kWarpsPerCta;
-        static bool attr_set[64] = {};  // function attributes are per device
-        int dev_id = 0;
-        XRB_CUDA(cudaGetDevice(&dev_id));
-        if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
-            XRB_CUDA(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
-        }
-        k_schur<<<point_grid(P.n_pts_local), kWarpsPerCta * 32, smem, st>>>(P, x, k, L, inv_radius, scalars);
-        XRB_LAUNCHED();
-    }
-    XRB_CUDA(cudaGetLastError());
-    return XRB_OK;
-}
-
-// =====================================================================================
-// 2'. Generation 2 of the Schur complement: no atomics.
+// 2. Schur complement without atomics.
 //   k_lin         point-major, one warp per point: phases A and B as in k_schur, then ONE
 //                 18-double record per observation, Tt_i = W_i (V + D^2)^-1/2, plus per
 //                 point (V + D^2)^-1 and h = (V + D^2)^-1 g.        (streaming writes only)
 //   k_gather      8 lanes per off-diagonal block (a, b): S_ab = - sum_{p in ab} Tt_i Tt_j^T
 //                 over the precomputed incidence list (ba_struct.cu), plain stores.
 //   k_cam_blocks  one CTA per camera: U_c = sum Jc^T Jc, g_c = sum Jc^T r,
-//                 rhs_c = sum Jc^T (r - JX h), S_cc -= sum Tt_i Tt_i^T, block-reduced.
+//                 rhs_c = sum Jc^T (r - JX h), Ud_c = sum Tt_i Tt_i^T, block-reduced.  It never
+//                 touches S, so it runs next to k_gather on a second stream; k_cam_diag (after the
+//                 exchange) folds U - Ud + D^2 into the diagonal blocks.
 // The result is deterministic (fixed summation order) and S is written exactly once.
 // =====================================================================================
 template <int LPP>
@@ -641,8 +447,12 @@ k_gather(BAProblemDev P, BALinSys L) {
     for (int j = 0; j < 36; ++j) acc[j] = 0.0;
     if (live) {
         const int i0 = P.blk_ptr[b], i1 = P.blk_ptr[b + 1];
+        // the index pair of the next incidence is requested before the records of this one:
+        // index -> record is a dependent load chain, one L2 round trip per link
+        int2 nxt = i0 + sub < i1 ? __ldg(P.inc + i0 + sub) : make_int2(0, 0);
         for (int it = i0 + sub; it < i1; it += kLanesPerBlock) {
-            const int2 oo = __ldg(P.inc + it);
+            const int2 oo = nxt;
+            if (it + kLanesPerBlock < i1) nxt = __ldg(P.inc + it + kLanesPerBlock);
             double Ti[18], Tj[18];
             load_rec(L.Tt, oo.x, Ti);
             load_rec(L.Tt, oo.y, Tj);
@@ -678,9 +488,9 @@ k_gather(BAProblemDev P, BALinSys L) {
         if (ra[a] < 0 || cb[c] < 0) continue;
         if (same) {
             if (c > a) continue;
-            L.S[(size_t)ra[a] * L.ld + cb[c]] = -(acc[a * 6 + c] + acc[c * 6 + a]);
+            L.S[L.tg.at(ra[a], cb[c])] = -(acc[a * 6 + c] + acc[c * 6 + a]);
         } else {
-            L.S[(size_t)ra[a] * L.ld + cb[c]] = -acc[e];
+            L.S[L.tg.at(ra[a], cb[c])] = -acc[e];
         }
     }
 }
@@ -752,12 +562,12 @@ k_cam_blocks(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L) {
                 if (j < 21)
                     L.U[(size_t)cols[a] * 6 + b] = v;
                 else
-                    L.S[(size_t)cols[a] * L.ld + cols[b]] -= v;  // += -Tt Tt^T on top of k_gather's part
+                    L.Ud[(size_t)cols[a] * 6 + b] = v;  // sum Tt Tt^T of the diagonal block: k_cam_diag subtracts it
             }
         } else if (j < 48) {
             if (cols[j - 42] >= 0) L.gc[cols[j - 42]] = v;
         } else {
-            if (cols[j - 48] >= 0) L.S[(size_t)P.nc * L.ld + cols[j - 48]] = v;  // rhs row
+            if (cols[j - 48] >= 0) L.rhs[cols[j - 48]] = v;
         }
     }
 }
@@ -785,7 +595,6 @@ __global__ void k_cam_diag(BAProblemDev P, BAStateDev x, BALinSys L, double inv_
     int cols[6];
 #pragma unroll
     for (int j = 0; j < 3; ++j) cols[j] = cq >= 0 ? cq + j : -1, cols[3 + j] = ct >= 0 ? ct + j : -1;
-    const int ld = L.ld;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
         if (cols[a] < 0) continue;
@@ -794,7 +603,7 @@ __global__ void k_cam_diag(BAProblemDev P, BAStateDev x, BALinSys L, double inv_
             if (cols[b] < 0) continue;
             double v = L.U[(size_t)cols[a] * 6 + b];
             if (a == b) v += fmin(fmax(v, 1e-6), 1e32) * inv_radius;
-            L.S[(size_t)cols[a] * ld + cols[b]] += v;
+            L.S[L.tg.at(cols[a], cols[b])] += v - L.Ud[(size_t)cols[a] * 6 + b];
         }
     }
     double gmax = 0.0;

@@ -193,9 +193,16 @@ int ba_build_structure(const xrb_ba_problem *P, int rank, int world, BAStructScr
         XRB_CUDA(cudaMemcpyAsync(ptr.data(), W.pt_ptr_g.p, ptr.size() * 4, cudaMemcpyDeviceToHost, st));
         XRB_CUDA(cudaStreamSynchronize(st));
         for (int p = 0; p < NP; ++p) kp[p] = ptr[p + 1] - ptr[p];
-        int32_t lo32 = 0, hi32 = NP;
-        if ((rc = xrb_ba_shard_range(NP, kp.data(), rank, world, &lo32, &hi32))) return rc;
-        p_lo = lo32, p_hi = hi32, o_lo = ptr[p_lo], o_hi = ptr[p_hi];
+        info->shard_lo.assign((size_t)world + 1, NP);
+        for (int r = 0; r < world; ++r) {
+            int32_t lo32 = 0, hi32 = NP;
+            if ((rc = xrb_ba_shard_range(NP, kp.data(), r, world, &lo32, &hi32))) return rc;
+            info->shard_lo[r] = lo32;
+            if (r == rank) p_lo = lo32, p_hi = hi32;
+        }
+        o_lo = ptr[p_lo], o_hi = ptr[p_hi];
+    } else {
+        info->shard_lo = {0, NP};
     }
     const int PL = p_hi - p_lo, OL = o_hi - o_lo;
     info->p_lo = p_lo, info->P_local = PL, info->O_local = OL;

@@ -66,6 +66,7 @@ struct BAStructBufs {  // outputs (owned by the solver)
 struct BAStructInfo {
     int nc, n_var_q, n_var_t, n_var_pts, n_res_blocks, bw;
     int p_lo, P_local, O_local;
+    std::vector<int32_t> shard_lo;  // [world + 1]: rank r owns points [shard_lo[r], shard_lo[r+1])
 };
 
 // Upload obs_cam/obs_pt/obs_uv and derive the structure for points [p_lo, p_hi) of this rank.
