@@ -32,9 +32,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GBA_ACCURATE = dict(function_tolerance=1e-5, parameter_tolerance=1e-6)  # ba_solver.cc:626-629
-
-
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -116,34 +113,55 @@ class _CudaPtr:
 # ------------------------------------------------------------------------------------------
 # BA arm
 # ------------------------------------------------------------------------------------------
-def make_c2(scale=1.0):
+_SCENE_KEYS = ("cam_q", "cam_t", "pts", "intr", "intr_model", "cam_intr", "obs_cam", "obs_pt", "obs_uv",
+               "cam_q_fixed", "cam_t_fixed", "pt_fixed")
+
+# option sets of the reference for each configuration
+GBA_ACCURATE = dict(function_tolerance=1e-5, parameter_tolerance=1e-6)                    # ba_solver.cc:626-629
+KGBA = dict(function_tolerance=1e-4, parameter_tolerance=1e-5, initial_radius=1e6)         # ba_solver.cc:667-670
+BA_CONFIGS = {
+    "C2": dict(options=GBA_ACCURATE, max_iterations=50,
+               workload="C2: synthetic 500-camera / 200k-point / 2M-obs global BA (GBA accurate options), "
+                        "SIMPLE_RADIAL, Huber 5.99, 2 translations fixed"),
+    "C4": dict(options=KGBA, max_iterations=20,
+               workload="C4: KITTI-shaped sequential scene, 2.7k cams / 1M pts / 10M obs (KGBA options: radius 1e6, "
+                        "<= 20 iterations), banded reduced camera system"),
+    "C5": dict(options=GBA_ACCURATE, max_iterations=50,
+               workload="C5: 1DSfM-shaped clustered scene, 5k cams (one camera model per image) / 1.5M pts / 12M obs, "
+                        "global BA (GBA accurate options)"),
+}
+
+
+def make_scene_cached(name, scale=1.0):
     from xrsfm_b200 import synth
-    cache = f"/tmp/xrsfm_b200_C2_{scale}.npz"
-    keys = ("cam_q", "cam_t", "pts", "intr", "intr_model", "cam_intr", "obs_cam", "obs_pt", "obs_uv",
-            "cam_q_fixed", "cam_t_fixed", "pt_fixed")
+    cache = f"/tmp/xrsfm_b200_{name}_{scale}.npz"
     if os.path.exists(cache):
         try:
             z = np.load(cache)
-            sc = synth.BAScene({k: np.ascontiguousarray(z[k]) for k in keys})
+            sc = synth.BAScene({k: np.ascontiguousarray(z[k]) for k in _SCENE_KEYS})
             sc.n_cams, sc.n_pts, sc.n_obs, sc.n_intr = (int(z["dims"][i]) for i in range(4))
             return sc
         except Exception:
             pass
-    sc = synth.make_scene("C2", scale)
+    sc = synth.make_scene(name, scale)
     try:  # atomic publish: several ranks may build the scene at the same time
         tmp = f"{cache}.{os.getpid()}.tmp.npz"
-        np.savez(tmp, dims=np.array([sc.n_cams, sc.n_pts, sc.n_obs, sc.n_intr]), **{k: sc[k] for k in keys})
+        np.savez(tmp, dims=np.array([sc.n_cams, sc.n_pts, sc.n_obs, sc.n_intr]), **{k: sc[k] for k in _SCENE_KEYS})
         os.replace(tmp, cache)
     except Exception:
         pass
     return sc
 
 
-def ba_gather_bytes(detail):
-    """Algorithmic HBM bytes of ONE launch of k_gather: per (block, point)
-    incidence two 144-byte observation records + the 8-byte index pair, per block the 6x6
-    result written once (288 B) + 12 B of block table."""
-    return int(detail["n_incidences"] * (2 * 144 + 8) + detail["n_blocks"] * (288 + 12))
+def make_c2(scale=1.0):
+    return make_scene_cached("C2", scale)
+
+
+def ba_gather_unique_bytes(detail, n_obs):
+    """UNIQUE HBM bytes of one k_gather launch: every 144-byte observation record read once, the
+    incidence index pairs (8 B) and the block table (12 B) read once, every 6x6 block of S written once.
+    The kernel requests each record k_p - 1 times; the re-reads are L2 business, not algorithmic bytes."""
+    return int(144 * n_obs + 8 * detail["n_incidences"] + (288 + 12) * detail["n_blocks"])
 
 
 def ba_lin_bytes(sc):
@@ -152,29 +170,74 @@ def ba_lin_bytes(sc):
     return 168 * sc.n_obs + 120 * sc.n_pts
 
 
+def ba_iteration_bytes(sc, detail):
+    """bytes per LM iteration = 72 O + 96 P + 8 (2 nnz(S) + 12 C)."""
+    nnz = 36.0 * detail["n_blocks"] + 21.0 * sc.n_cams
+    return 72.0 * sc.n_obs + 96.0 * sc.n_pts + 8.0 * (2.0 * nnz + 12.0 * sc.n_cams)
+
+
 def ba_chol_flops(nc, bw):
-    """Blocked Cholesky + forward/backward substitution, banded: n*bw^2 (dense: n^3/3) FMAs x 2."""
+    """Cholesky + forward/backward substitution, banded: n*bw^2 (dense: n^3/3) FMAs x 2."""
     if bw >= nc - 1:
         return 2.0 * (nc ** 3 / 6.0 + nc ** 2)
     return 2.0 * (nc * bw * bw / 2.0 + 2.0 * nc * bw)
 
 
-def run_ba(args, rank, world, local_rank):
+def load_fp64_peak():
+    """Measured FP64 FMA-pipe peak of this pool's B200 (tools/fp64_peak.cu, committed copy)."""
+    p = os.path.join(ROOT, "profiles", "r02_fp64_peak.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dfma_tflops"]), float(d["dmma_m8n8k4_tflops"]), "measured (profiles/r02_fp64_peak.json)"
+    except Exception:
+        return 37.0, 37.0, "nominal"
+
+
+def setup_exchange(solver, rank, world, local_rank):
+    """Multi-GPU: the library's own NCCL communicator (xrb_ba_comm_init); torch.distributed only
+    ships the 128-byte id."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+
+    def bcast(raw):
+        t = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+
+    solver.comm_init(rank, world, bcast)
+
+
+def parity_check(sc, cfg, n_iters, gpu_log):
+    """Outside every timed region: the first iterations of the CPU oracle on the same scene against
+    the GPU's iteration log (cost 1e-7 relative, same accept/reject decisions)."""
+    from tests import oracle_lib as ol
+    ref = sc.copy_state()
+    s = ol.ba_solve(ref, ol.ba_options(max_iterations=n_iters, **cfg["options"]), host_cores())
+    n = min(s.n_iterations_logged, len(gpu_log), n_iters + 1)
+    worst = 0.0
+    for i in range(n):
+        a, b = s.iterations[i], gpu_log[i]
+        if a.step_is_successful != b["step_is_successful"]:
+            return {"parity_checked": False, "why": f"accept/reject differs at iteration {i}"}
+        worst = max(worst, abs(a.cost - b["cost"]) / max(abs(a.cost), 1e-300))
+    return {"parity_checked": bool(worst < 1e-7), "iterations_compared": n, "max_rel_cost_diff": worst,
+            "against": "CPU oracle (oracle/ba_oracle.cpp), same scene and options"}
+
+
+def run_ba(args, rank, world, local_rank, name="C2"):
     import torch
     from xrsfm_b200 import _lib, ba
+    cfg = BA_CONFIGS[name]
+    opts = cfg["options"]
     torch.cuda.set_device(local_rank)
-    sc = make_c2(args.scale)
+    sc = make_scene_cached(name, args.scale)
     solver = ba.BASolver(device=local_rank)
     solver._ensure()
-    if world > 1:
-        import torch.distributed as dist
-
-        def allreduce(ptr, count):
-            t = torch.as_tensor(_CudaPtr(ptr, count), device=f"cuda:{local_rank}")
-            dist.all_reduce(t)
-            torch.cuda.current_stream().synchronize()
-
-        solver.set_exchange(rank, world, allreduce)
+    setup_exchange(solver, rank, world, local_rank)
     lib = _lib.lib()
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -184,10 +247,18 @@ def run_ba(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        if world <= 1:
+            return v
+        import torch.distributed as dist
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # -- resident path: load once, W warm-up iterations, then exactly K timed iterations
     solver.load(sc)
     if args.warmup > 0:
-        solver.run(stream=stream, max_iterations=args.warmup, fixed_iterations=1, **GBA_ACCURATE)
+        solver.run(stream=stream, max_iterations=args.warmup, fixed_iterations=1, **opts)
     solver.reset()
     clocks = ClockSampler(local_rank)
     barrier()
@@ -196,93 +267,116 @@ def run_ba(args, rank, world, local_rank):
     launches0 = lib.xrb_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    summ = solver.run(stream=stream, max_iterations=args.steps, fixed_iterations=1, **GBA_ACCURATE)
+    summ = solver.run(stream=stream, max_iterations=args.steps, fixed_iterations=1, **opts)
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.xrb_kernel_launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
     prof = solver.profile()
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    detail = solver.profile_detail()
     assert summ.num_lm_iterations == args.steps, (summ.num_lm_iterations, args.steps)
 
-    # -- to-convergence run (reported, not timed as the metric)
+    # -- to-convergence run with the reference's option set (reported; its log feeds the parity check)
     solver.reset()
-    conv = solver.run(stream=stream, max_iterations=50, **GBA_ACCURATE)
+    conv = solver.run(stream=stream, max_iterations=cfg["max_iterations"], **opts)
+    conv_log = [{"cost": conv.iterations[i].cost, "step_is_successful": conv.iterations[i].step_is_successful}
+                for i in range(conv.n_iterations_logged)]
     barrier()
 
-    # -- e2e: host buffers through xrb_ba_solve (upload + K iterations + download)
+    # -- e2e: host buffers through xrb_ba_solve (upload + structure build + K iterations + download)
     work = sc.copy_state()
     for k in ("cam_q", "cam_t", "pts"):
         work[k] = np.ascontiguousarray(work[k])
-    h2d = sum(sc[k].nbytes for k in ("cam_q", "cam_t", "pts", "intr", "intr_model", "cam_intr", "obs_cam",
-                                      "obs_pt", "obs_uv", "cam_q_fixed", "cam_t_fixed", "pt_fixed"))
+    h2d = sum(sc[k].nbytes for k in _SCENE_KEYS)
     d2h = sum(sc[k].nbytes for k in ("cam_q", "cam_t", "pts"))
     barrier()
     t0 = time.perf_counter()
-    s_e2e = solver.solve_scene(work, max_iterations=args.steps, fixed_iterations=1, **GBA_ACCURATE)
+    s_e2e = solver.solve_scene(work, max_iterations=args.steps, fixed_iterations=1, **opts)
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    # the same call for a REAL solve: to convergence, nothing amortised
+    work2 = sc.copy_state()
+    barrier()
+    t0 = time.perf_counter()
+    s_full = solver.solve_scene(work2, max_iterations=cfg["max_iterations"], **opts)
+    barrier()
+    full_s = max_over_ranks(time.perf_counter() - t0)
     if rank != 0:
         return None
-    peak, peak_src = load_peaks()
-    detail = solver.profile_detail() if rank == 0 else {}
+
     nsolve = max(1.0, detail["solves"])
     kern_ms = {"k_lin": detail["lin_ms"] / nsolve, "k_gather": detail["gather_ms"] / nsolve,
-               "k_cam_blocks": detail["cam_blocks_ms"] / nsolve, "cholesky_graph": prof["solve"][0] / nsolve}
-    gather_bytes = ba_gather_bytes(detail)
-    ach = gather_bytes / (kern_ms["k_gather"] * 1e-3) / 1e9
-    chol_tflops = ba_chol_flops(detail["nc"], detail["half_bandwidth"]) / (kern_ms["cholesky_graph"] * 1e-3) / 1e12
+               "k_cam_blocks_exposed": detail["cam_blocks_ms"] / nsolve, "tile_cholesky+backsolve": prof["solve"][0] / nsolve}
+    per_it = {k: v[0] / nsolve for k, v in prof.items() if k != "run"}
     out = {
         "metric": "BA LM-iterations/sec", "value": args.steps / (ms * 1e-3), "unit": "LM-iterations/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "C2: synthetic 500-camera / 200k-point / 2M-obs global BA (GBA accurate options), "
-                               "SIMPLE_RADIAL, Huber 5.99, 2 translations fixed",
+        "config": {"workload": cfg["workload"], "name": name,
                    "n_cams": sc.n_cams, "n_pts": sc.n_pts, "n_obs": sc.n_obs, "scale": args.scale,
-                   "parallelism": f"points sharded over {world} GPU(s), cameras replicated, "
-                                  "SUM all-reduce of the reduced camera system per solve",
+                   "parallelism": f"points sharded over {world} GPU(s), cameras replicated, one in-library "
+                                  "ncclAllReduce(ncclDouble, ncclSum) of the packed reduced camera system per solve",
                    "l2_note": "no explicit L2 flush: every iteration streams a working set larger than the 126 MB L2 "
-                              "(observations 48 MB + per-observation records 288 MB + reduced system 72 MB + points)",
+                              "(observation records 144 B/obs + observations 24 B/obs + reduced system + points)",
+                   "reduced_system": {"dimension": int(detail["nc"]), "half_bandwidth": int(detail["half_bandwidth"]),
+                                      "blocks": int(detail["n_blocks"])},
                    "iterations_to_convergence": conv.num_lm_iterations,
                    "termination": ba.TERMINATION.get(conv.termination_type),
                    "final_rms_px": float(np.sqrt(conv.final_cost / max(1, conv.num_residuals_reduced))),
-                   "phase_ms_per_iteration": {k: v[0] / max(1, args.steps + 1) for k, v in prof.items() if k != "run"}},
+                   "phase_ms_per_iteration": per_it},
         "e2e": {"value": args.steps / e2e_s, "unit": "LM-iterations/s", "h2d_bytes_per_step": h2d / args.steps,
                 "d2h_bytes_per_step": d2h / args.steps, "call": "xrb_ba_solve (host buffers in/out)",
-                "iterations": s_e2e.num_lm_iterations},
+                "iterations": s_e2e.num_lm_iterations,
+                "to_convergence": {"value": s_full.num_lm_iterations / full_s, "unit": "LM-iterations/s",
+                                   "iterations": s_full.num_lm_iterations, "seconds": full_s,
+                                   "note": "one real solve through xrb_ba_solve: upload + structure build + every "
+                                           "iteration to the reference's tolerances + download, nothing amortised"}},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"kernel": "k_gather (Schur complement: per-block gather of the observation records)",
-                     "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": ach / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one k_gather launch on this
-                     # very scene, from the ncu --set full capture summarised in profiles/
-                     "traffic": 1.355e9 if args.scale == 1.0 else None,
-                     "traffic_source": "profiles/r01c_gather_and_update_summary.md",
-                     "algorithmic_bytes_per_launch": gather_bytes,
-                     "ms_per_launch": kern_ms["k_gather"],
-                     "note": "HBM-bound kernel of the iteration; the largest share of the time is the FP64 "
-                             "Cholesky (see roofline_fp64), which is bound by the FP64 FMA pipe, not HBM"},
-        "roofline_fp64": {"kernel": "blocked Cholesky + substitutions (CUDA graph)", "bound": "fp64 FMA pipe",
-                          "achieved": chol_tflops, "peak": 37.0, "peak_source": "nominal (B200 FP64, no measured figure "
-                          "in MEASURED_PEAKS.json)", "unit": "TFLOP/s", "frac": chol_tflops / 37.0,
-                          "ms_per_launch": kern_ms["cholesky_graph"]},
         "kernel_ms_per_solve": kern_ms,
-        "lin_roofline": {"kernel": "k_lin", "bound": "hbm", "achieved": ba_lin_bytes(sc) / (kern_ms["k_lin"] * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s"},
+        "_scene": sc, "_detail": detail, "_conv_log": conv_log, "_cfg": cfg,
     }
+    return out
+
+
+def ba_rooflines(out):
+    """roofline = the step's dominant kernel; HBM figures use UNIQUE bytes (never more than DRAM traffic)."""
+    sc, detail, kern_ms = out["_scene"], out["_detail"], out["kernel_ms_per_solve"]
+    hbm_peak, peak_src = load_peaks()
+    dfma, dmma, fsrc = load_fp64_peak()
+    step_ms = out["ms_per_step"]
+    chol_ms = kern_ms["tile_cholesky+backsolve"]
+    chol_tf = ba_chol_flops(detail["nc"], detail["half_bandwidth"]) / (chol_ms * 1e-3) / 1e12
+    gat_b = ba_gather_unique_bytes(detail, sc.n_obs)
+    gat_ach = gat_b / (kern_ms["k_gather"] * 1e-3) / 1e9
+    it_b = ba_iteration_bytes(sc, detail)
+    roof = {"kernel": "k_tile_cholesky + k_tile_backsolve (persistent tile-DAG Cholesky of the reduced camera system)",
+            "bound": "fp64 FMA pipe (a dense contraction in FP64: neither HBM nor the low-precision tensor pipe)",
+            "achieved": chol_tf, "peak": dfma, "peak_source": fsrc, "unit": "TFLOP/s", "frac": chol_tf / dfma,
+            "share_of_step": chol_ms / step_ms, "ms_per_launch": chol_ms, "traffic": None,
+            "algorithmic_flops_per_launch": ba_chol_flops(detail["nc"], detail["half_bandwidth"]),
+            "tensor_pipe_note": f"FP64 tensor (DMMA m8n8k4) peak measured at {dmma:.1f} TFLOP/s vs {dfma:.1f} for DFMA on this "
+                                "part; the kernel issues DFMA"}
+    out["roofline"] = roof
+    out["roofline_hbm"] = {
+        "kernel": "k_gather (Schur complement: per-block gather of the observation records)", "bound": "hbm",
+        "achieved": gat_ach, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": gat_ach / hbm_peak,
+        "share_of_step": kern_ms["k_gather"] / step_ms, "ms_per_launch": kern_ms["k_gather"],
+        "algorithmic_bytes_per_launch": gat_b, "traffic": None,
+        "traffic_note": "measured dram__bytes of this kernel: see the ncu summary under profiles/ (r01c: 1.355e9 B per "
+                        "launch at C2 against 0.41e9 unique: the records are re-read k_p - 1 times, about half from L2)"}
+    out["roofline_iteration"] = {
+        "bound": "hbm", "unit": "GB/s", "bytes_per_iteration_survey_8d": it_b,
+        "achieved": it_b / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "frac": it_b / (step_ms * 1e-3) / 1e9 / hbm_peak}
+    out["lin_roofline"] = {"kernel": "k_lin", "bound": "hbm", "achieved": ba_lin_bytes(sc) / (kern_ms["k_lin"] * 1e-3) / 1e9,
+                           "peak": hbm_peak, "unit": "GB/s"}
+
+
+def strip_private(out):
+    for k in [k for k in out if k.startswith("_")]:
+        del out[k]
     return out
 
 
@@ -290,13 +384,13 @@ def cpu_baseline_ba(args, sample_iters=2):
     """The CPU oracle (Ceres-faithful port; the reference's Ceres cannot be built here) on the
     host cores, same C2 scene, bounded sample of LM iterations."""
     from tests import oracle_lib as ol
-    sc = make_c2(args.scale)
+    sc = make_scene_cached(args.config, args.scale)
     cores = host_cores()
     t0 = time.perf_counter()
-    s = ol.ba_solve(sc, ol.ba_options(max_iterations=sample_iters, fixed_iterations=1, **GBA_ACCURATE), cores)
+    s = ol.ba_solve(sc, ol.ba_options(max_iterations=sample_iters, fixed_iterations=1, **BA_CONFIGS[args.config]["options"]), cores)
     dt = time.perf_counter() - t0
     return {"value": s.num_lm_iterations / dt, "unit": "LM-iterations/s", "cores": cores, "kind": "port",
-            "sample": f"{s.num_lm_iterations} LM iterations of the C2 scene with the CPU oracle "
+            "sample": f"{s.num_lm_iterations} LM iterations of the {args.config} scene with the CPU oracle "
                       f"(oracle/ba_oracle.cpp, OpenMP {cores} threads), {dt:.1f} s"}
 
 
@@ -444,28 +538,30 @@ def reference_cuda_matcher(n_feat=4096, n=40):
 def reference_arm(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path on the host cores.
     The reference's BA is Ceres (un-vendored, not buildable here) -> the Ceres-faithful oracle
-    port; rank 0 alone runs it."""
+    port; rank 0 alone runs it.  Same workload, steps and warm-up as the native arm (one LM iteration
+    of C2 is under a second on the box's cores, so nothing has to be cut)."""
     if rank != 0:
         return None
     from tests import oracle_lib as ol
+    cfg = BA_CONFIGS["C2"]
     sc = make_c2(args.scale)
     cores = host_cores()
-    steps = max(1, min(args.steps, 4))  # bounded sample: ~2-3 s per LM iteration on 8 cores
-    warm = sc.copy_state()
-    ol.ba_solve(warm, ol.ba_options(max_iterations=min(1, args.warmup), fixed_iterations=1, **GBA_ACCURATE), cores)
+    if args.warmup > 0:
+        warm = sc.copy_state()
+        ol.ba_solve(warm, ol.ba_options(max_iterations=args.warmup, fixed_iterations=1, **cfg["options"]), cores)
     t0 = time.perf_counter()
-    s = ol.ba_solve(sc, ol.ba_options(max_iterations=steps, fixed_iterations=1, **GBA_ACCURATE), cores)
+    s = ol.ba_solve(sc, ol.ba_options(max_iterations=args.steps, fixed_iterations=1, **cfg["options"]), cores)
     dt = time.perf_counter() - t0
     v = s.num_lm_iterations / dt
     return {
         "impl": "reference", "metric": "BA LM-iterations/sec", "value": v, "unit": "LM-iterations/s",
-        "n_gpus": world, "steps": s.num_lm_iterations, "warmup": min(1, args.warmup),
+        "n_gpus": world, "steps": s.num_lm_iterations, "warmup": args.warmup,
         "ms_per_step": dt / s.num_lm_iterations * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: synthetic 500-camera / 200k-point / 2M-obs global BA (GBA accurate options)",
+        "config": {"workload": cfg["workload"], "name": "C2",
                    "n_cams": sc.n_cams, "n_pts": sc.n_pts, "n_obs": sc.n_obs, "scale": args.scale},
         "cpu_baseline": {"value": v, "unit": "LM-iterations/s", "cores": cores, "kind": "port",
-                         "sample": f"{s.num_lm_iterations} LM iterations (of {args.steps} requested) of the C2 scene, "
+                         "sample": f"{s.num_lm_iterations} LM iterations of the C2 scene, "
                                    "CPU oracle = Ceres-faithful restatement; Ceres itself is un-vendored and "
                                    "not buildable in this image"},
         "e2e": {"value": v, "unit": "LM-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -480,7 +576,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--path", default="both", choices=["both", "ba", "match"])
-    ap.add_argument("--scale", type=float, default=1.0, help="shrink C2 (tests only; 1.0 = the named config)")
+    ap.add_argument("--config", default="C2", choices=sorted(BA_CONFIGS), help="BA scene of the headline line")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 object next to the C2 headline")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the BA scene (tests only; 1.0 = the named config)")
     ap.add_argument("--match-images", type=int, default=2000, help="images of the matching leg (C3 = 2000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -499,7 +597,20 @@ def main():
         dist.init_process_group(os.environ.get("XRB_BENCH_BACKEND", "nccl"))
     out = None
     if args.path in ("both", "ba"):
-        out = run_ba(args, rank, world, local_rank)
+        out = run_ba(args, rank, world, local_rank, args.config)
+        c4 = None
+        if args.config == "C2" and not args.no_c4 and args.scale == 1.0:
+            c4 = run_ba(args, rank, world, local_rank, "C4")
+        if rank == 0:
+            ba_rooflines(out)
+            if not args.no_cpu_baseline:
+                out.update(parity_check(out["_scene"], out["_cfg"], 3, out["_conv_log"]))
+            if c4 is not None:
+                ba_rooflines(c4)
+                keep = ("value", "unit", "ms_per_step", "steps", "n_gpus", "config", "e2e", "kernel_ms_per_solve",
+                        "roofline", "gpu_launches")
+                out["c4"] = {k: c4[k] for k in keep}
+            strip_private(out)
     mt = None
     if args.path in ("both", "match"):
         mt = run_match(args, rank, world, local_rank)

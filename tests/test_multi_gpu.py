@@ -1,5 +1,6 @@
 """2-GPU test of the BA exchange path (points sharded, SUM all-reduce of the reduced camera
-system over NCCL) and of pair-sharded matching.  Needs >= 2 GPUs: run with
+system over NCCL — the library's own communicator, and the caller-hook variant) and of
+pair-sharded matching.  Needs >= 2 GPUs: run with
 `gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu`."""
 import os
 import socket
@@ -26,7 +27,7 @@ class _CudaPtr:
         self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, mode="native"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -38,12 +39,23 @@ def _worker(rank, world, port, q):
         work = sc.copy_state()
         solver = ba.BASolver(device=rank)
 
-        def allreduce(ptr, count):
-            t = torch.as_tensor(_CudaPtr(ptr, count), device=f"cuda:{rank}")
-            dist.all_reduce(t)
-            torch.cuda.current_stream().synchronize()
+        if mode == "native":
+            def bcast(raw):
+                t = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{rank}")
+                if rank == 0:
+                    t.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+                dist.broadcast(t, 0)
+                return bytes(t.cpu().numpy().tobytes())
 
-        solver.set_exchange(rank, world, allreduce)
+            solver.comm_init(rank, world, bcast)
+        else:
+            def allreduce(ptr, count, stream):
+                # the contract: the reduction is ordered on the solver's stream, no host sync
+                t = torch.as_tensor(_CudaPtr(ptr, count), device=f"cuda:{rank}")
+                with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+                    dist.all_reduce(t)
+
+            solver.set_exchange(rank, world, allreduce)
         s = solver.solve_scene(work, **ol.GBA_ACCURATE)
         # matching: each rank matches its share of the pair list
         imgs, _ = synth.make_images(6, 600, seed=9)
@@ -61,7 +73,8 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_gpu_ba_equals_single_gpu_and_oracle():
+@pytest.mark.parametrize("mode", ["native", "hook"])
+def test_two_gpu_ba_equals_single_gpu_and_oracle(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from tests import oracle_lib as ol
@@ -70,7 +83,7 @@ def test_two_gpu_ba_equals_single_gpu_and_oracle():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda r: r[0])
@@ -87,7 +100,7 @@ def test_two_gpu_ba_equals_single_gpu_and_oracle():
         assert term == s1.termination_type == s_ref.termination_type
         assert iters == s1.num_lm_iterations == s_ref.num_lm_iterations
         assert cost == pytest.approx(s1.final_cost, rel=1e-9)
-        # every rank returns every point (shards gathered through the hook)
+        # every rank returns every point (shards gathered: grouped ncclBroadcast / hook)
         assert np.abs(X_ - single.pts).max() <= 1e-8 * max(1.0, np.abs(single.pts).max())
         assert np.abs(q_ - single.cam_q).max() <= 1e-9 and np.abs(t_ - single.cam_t).max() <= 1e-8
         assert np.abs(X_ - ref.pts).max() <= 1e-5 * max(1.0, np.abs(ref.pts).max())

@@ -175,9 +175,11 @@ def _finish_scene(rng, Rs, qs, ts, centres, X, obs_cam, obs_pt, intr, width, hei
     obs_cam, obs_pt = obs_cam[order].astype(np.int32), obs_pt[order].astype(np.int32)
     n_obs = obs_cam.shape[0]
     uv = np.empty((n_obs, 2))
+    by_cam = np.argsort(obs_cam, kind="stable")  # one pass instead of one mask per camera
+    start = np.searchsorted(obs_cam[by_cam], np.arange(n_cams + 1))
     for c in range(n_cams):
-        m = obs_cam == c
-        if m.any():
+        m = by_cam[start[c]: start[c + 1]]
+        if m.size:
             uv[m], _ = project_simple_radial(Rs[c], ts[c], X[obs_pt[m]], intr)
     uv += rng.normal(0.0, noise_px, size=uv.shape)
     n_out = int(round(outlier_frac * n_obs))
@@ -209,8 +211,9 @@ def _finish_scene(rng, Rs, qs, ts, centres, X, obs_cam, obs_pt, intr, width, hei
     X0 = X + rng.normal(0.0, 1.0, size=X.shape) * (0.01 * mean_depth)[:, None]
     n_behind = int(round(behind_frac * n_pts))
     if n_behind:
+        first = np.searchsorted(obs_pt, np.arange(n_pts + 1))  # obs_pt is sorted (lexsort above)
         for p in rng.choice(n_pts, size=n_behind, replace=False):
-            o = np.flatnonzero(obs_pt == p)
+            o = np.arange(first[p], first[p + 1])
             if o.size == 0:
                 continue
             c = obs_cam[rng.choice(o)]
