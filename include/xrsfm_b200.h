@@ -269,6 +269,15 @@ int xrb_ba_profile(const xrb_ba_solver *s, double ms[6], int64_t launches[6]);
 int xrb_debug_chol_trace(int enable, int64_t *out, int cap_records);
 int xrb_debug_tile_solve(int n, int bw, const double *A, const double *rhs, double *x_out, int reps,
                          double *ms_out);
+/* Host-only debug hooks (no device needed): the symbolic plan (tile slots, task lists with the flag
+ * values they wait for) of a tile pattern pat[nt x nt] (lower part), and the column order of a band.
+ * counts[16] = nt, n_tiles, n_tiles_orig, n_f, n_w, n_b, n_wb, n_far, n_chain_f, n_chain_b, depth_f,
+ * depth_b; output arrays may be null and are filled up to their capacity in int32 elements. */
+int xrb_debug_chol_plan(int nt, const uint8_t *pat, int32_t *counts, int32_t *tab, int32_t *ftasks, int cap_f,
+                        int32_t *wtasks, int cap_w, int32_t *btasks, int cap_b, int32_t *wbtasks, int cap_wb,
+                        int32_t *far_rows, int32_t *far_slots, int cap_far);
+int xrb_debug_column_order(int n_cams, const int32_t *widths, int bw, int allow_nd, int32_t *start, int32_t *n_pad,
+                           int32_t *parts);
 
 /* Finer split of the last run, out[n >= 8]: [0..2] total ms of k_lin (+ memsets), k_gather,
  * k_cam_blocks; [3] linear solves executed; [4] off-diagonal 6x6 blocks of the reduced camera

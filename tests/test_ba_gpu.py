@@ -263,3 +263,55 @@ def test_degenerate_structure(solver):
     sc4["n_obs"] = 0
     s4 = solver.solve_scene(sc4, **ol.GBA_FAST)
     assert s4.termination_type == 0 and s4.num_residuals_reduced == 0
+
+
+def test_c2_full_size_to_convergence(solver):
+    """BASELINE config C2 at its full size (500 cams / 200k pts / 2M obs, the bench headline): the whole
+    trajectory to convergence against the oracle — termination, iteration count, every logged cost,
+    solved poses / points and residuals within 1e-5."""
+    import os
+    sc = synth.make_scene("C2")
+    ref, got = sc.copy_state(), sc.copy_state()
+    s_ref = ol.ba_solve(ref, ol.ba_options(**ol.GBA_ACCURATE), os.cpu_count() or 1)
+    s_got = solver.solve_scene(got, **ol.GBA_ACCURATE)
+    _compare_logs(s_got, s_ref, rel=1e-6)
+    _compare_states(got, ref)
+    assert s_got.final_cost == pytest.approx(s_ref.final_cost, rel=1e-7)
+    solver.load(got)
+    r_got = solver.residuals()
+    r_ref = ol.ba_residuals(ref, ol.ba_options())
+    assert np.abs(r_got - r_ref).max() <= REL * max(1.0, np.abs(r_ref).max())
+    d = solver.profile_detail()
+    assert d["parts"] == 1 and d["tiles"] == d["tiles_original"] == 47 * 48 // 2  # dense: natural order, no fill
+
+
+def test_c4_shaped_scene_dissected_order(solver, monkeypatch):
+    """BASELINE config C4 (KITTI-shaped, KGBA options ba_solver.cc:665-670) at 0.15 scale: 405 cameras, a
+    narrow-banded reduced system, so the plan dissects the band (ba_plan.cu).  The scene is ill-conditioned
+    at radius 1e6 (forward motion, 0.1 % of the points barely constrained): S = U - W V^-1 W^T cancels ten
+    digits, and two correct FP64 solvers part ways after a few iterations (the oracle with 1 and with 4
+    threads differs by 2e-7 at iteration 2).  Hence: the first iterations against the oracle within 1e-5, and
+    the dissected order against the natural order — same S, different elimination — much tighter."""
+    import os
+    sc = synth.make_scene("C4", 0.15)
+    opts = dict(ol.KGBA)
+    opts["max_iterations"] = 8
+    got = sc.copy_state()
+    s_nd = solver.solve_scene(got, **opts)
+    d = solver.profile_detail()
+    assert d["parts"] >= 3 and d["chains"] >= 3 and d["depth_factor"] < d["tile_columns"]
+    ref = sc.copy_state()
+    s_ref = ol.ba_solve(ref, ol.ba_options(**opts), os.cpu_count() or 1)
+    for i in range(4):
+        a, b = s_nd.iterations[i], s_ref.iterations[i]
+        assert a.step_is_successful == b.step_is_successful, i
+        assert a.cost == pytest.approx(b.cost, rel=1e-5 if i < 2 else 1e-4), i
+    monkeypatch.setenv("XRB_BA_ORDER", "natural")
+    nat = sc.copy_state()
+    s_nat = ba.BASolver().solve_scene(nat, **opts)
+    assert s_nat.n_iterations_logged == s_nd.n_iterations_logged
+    for i in range(s_nd.n_iterations_logged):
+        a, b = s_nd.iterations[i], s_nat.iterations[i]
+        assert a.step_is_successful == b.step_is_successful, i
+        assert a.cost == pytest.approx(b.cost, rel=1e-6), i
+    assert np.abs(got.cam_q - nat.cam_q).max() < 1e-5

@@ -103,6 +103,9 @@ SIGNATURES = {
     "xrb_ba_profile_detail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "xrb_debug_chol_trace": (C.c_int, [C.c_int, C.c_void_p, C.c_int]),
     "xrb_debug_tile_solve": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "xrb_debug_chol_plan": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "xrb_debug_column_order": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xrb_ftr_scan": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xrb_ftr_read": (C.c_int, [C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xrb_ftr_write": (C.c_int, [C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

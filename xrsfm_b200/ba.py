@@ -153,9 +153,11 @@ class BASolver:
         return {n: (ms[i], ln[i]) for i, n in enumerate(names)}
 
     def profile_detail(self):
-        out = (C.c_double * 8)()
-        _lib.check(_lib.lib().xrb_ba_profile_detail(self._h, out, 8), "xrb_ba_profile_detail")
-        keys = ("lin_ms", "gather_ms", "cam_blocks_ms", "solves", "n_blocks", "n_incidences", "nc", "half_bandwidth")
+        out = (C.c_double * 16)()
+        _lib.check(_lib.lib().xrb_ba_profile_detail(self._h, out, 16), "xrb_ba_profile_detail")
+        keys = ("lin_ms", "gather_ms", "cam_blocks_ms", "solves", "n_blocks", "n_incidences", "nc", "half_bandwidth",
+                "parts", "tile_columns", "tiles", "tiles_original", "plan_flops", "depth_factor", "depth_backward",
+                "chains")
         return dict(zip(keys, list(out)))
 
     def comm_init(self, rank, world, broadcast_bytes):

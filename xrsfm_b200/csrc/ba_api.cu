@@ -51,8 +51,11 @@ struct xrb_ba_solver {
     bool loaded = false;
     int C = 0, P_total = 0, O_total = 0, n_intr = 0;
     int P_local = 0, O_local = 0, p_lo = 0;
-    int nc = 0, bw = 0;
-    TileGeom tg;
+    int nc = 0, bw = 0;       // nc: padded dimension of the reduced camera system (a multiple of 64)
+    int nc_true = 0, parts = 1;  // variable camera columns; independent interiors of the column order
+    CholPlan plan;
+    DevBuf d_holes, d_pat;
+    int n_holes = 0;
     int n_var_q = 0, n_var_t = 0, n_var_pts = 0, n_res_blocks = 0;
 
     // device: problem
@@ -66,10 +69,12 @@ struct xrb_ba_solver {
     // device: states
     DevBuf d_q[3], d_t[3], d_X[3];  // 0 = current, 1 = candidate, 2 = initial copy
     int cur = 0;
-    // device: linear system.  E = [S tiles | rhs | U | Ud | gc | scalE(8) | slots(world) | n2c]: everything
-    // one linear solve exchanges is one contiguous prefix (n2c travels once, at iteration 0)
+    // device: linear system.  E = [rhs | U | Ud | gc | scalE(8) | slots(world) | S tiles (original, then
+    // fill) | n2c]: everything one linear solve exchanges is one contiguous prefix that ends with the
+    // structurally non-zero tiles of S (the fill is zero on every rank; n2c travels once, at iteration 0)
     DevBuf d_E, d_Vinv, d_gp, d_sc, d_sp, d_linv, d_yc, d_step_p, d_scal, d_full;
-    size_t off_rhs = 0, off_U = 0, off_Ud = 0, off_gc = 0, off_n2c = 0, off_scalE = 0, off_slots = 0, E_count = 0;
+    size_t off_rhs = 0, off_U = 0, off_Ud = 0, off_gc = 0, off_n2c = 0, off_scalE = 0, off_slots = 0, off_S = 0,
+           off_exch_end = 0, E_count = 0;
     double *h_scal = nullptr;  // pinned mirror: [scalE(8) | slots(world) | scal2(8) | scalL(8)]
 
     double ms[6] = {0, 0, 0, 0, 0, 0};
@@ -94,7 +99,7 @@ struct xrb_ba_solver {
     BALinSys linsys() const {
         BALinSys L;
         double *E = d_E.as<double>();
-        L.S = E, L.tg = tg, L.rhs = E + off_rhs, L.U = E + off_U, L.Ud = E + off_Ud, L.gc = E + off_gc, L.n2c = E + off_n2c;
+        L.S = E + off_S, L.tm.nt = plan.d.nt, L.tm.tab = plan.d.tab, L.rhs = E + off_rhs, L.U = E + off_U, L.Ud = E + off_Ud, L.gc = E + off_gc, L.n2c = E + off_n2c;
         L.Vinv = d_Vinv.as<double>(), L.gp = d_gp.as<double>();
         L.sc = d_sc.as<double>(), L.sp = d_sp.as<double>();
         L.Tt = d_Tt.as<double>(), L.h = d_h.as<double>();
@@ -188,6 +193,58 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
     s->p_lo = info.p_lo, s->P_local = info.P_local, s->O_local = info.O_local;
     s->shard_lo = info.shard_lo;
     lt.lap("structure (device)");
+    // ---- column order, tile pattern, symbolic factorisation (ba_plan.cu)
+    {
+        std::vector<int> widths, cam_of;
+        for (int c = 0; c < C; ++c) {
+            const int w = (info.h_colq[c] >= 0 ? 3 : 0) + (info.h_colt[c] >= 0 ? 3 : 0);
+            if (w) widths.push_back(w), cam_of.push_back(c);
+        }
+        std::vector<int32_t> start;
+        int n_pad = 64, parts = 1;
+        const char *order_env = getenv("XRB_BA_ORDER");
+        const bool allow_nd = !(order_env && strcmp(order_env, "natural") == 0);
+        plan_column_order(widths, info.bw, allow_nd, start, n_pad, parts);
+        std::vector<uint8_t> covered((size_t)n_pad, 0);
+        for (size_t v = 0; v < cam_of.size(); ++v) {
+            const int c = cam_of[v];
+            int at = start[v];
+            if (info.h_colq[c] >= 0) info.h_colq[c] = at, at += 3;
+            if (info.h_colt[c] >= 0) info.h_colt[c] = at, at += 3;
+            for (int j = start[v]; j < at; ++j) covered[j] = 1;
+        }
+        std::vector<int32_t> holes;
+        for (int j = 0; j < n_pad; ++j)
+            if (!covered[j]) holes.push_back(j);
+        s->nc_true = info.nc, s->nc = n_pad, s->parts = parts, s->n_holes = (int)holes.size();
+        const int nt = n_pad / 64;
+        if (C) {
+            XRB_CUDA(cudaMemcpyAsync(s->d_colq.p, info.h_colq.data(), (size_t)C * 4, cudaMemcpyHostToDevice, st));
+            XRB_CUDA(cudaMemcpyAsync(s->d_colt.p, info.h_colt.data(), (size_t)C * 4, cudaMemcpyHostToDevice, st));
+        }
+        if ((rc = s->d_holes.reserve(std::max<size_t>(1, holes.size()) * 4))) return rc;
+        if (!holes.empty())
+            XRB_CUDA(cudaMemcpyAsync(s->d_holes.p, holes.data(), holes.size() * 4, cudaMemcpyHostToDevice, st));
+        if ((rc = s->d_pat.reserve((size_t)nt * nt))) return rc;
+        XRB_CUDA(cudaMemsetAsync(s->d_pat.p, 0, (size_t)nt * nt, st));
+        if ((rc = launch_tile_pattern(NP, s->W.pt_ptr_g.as<int32_t>(), s->W.vals.as<int32_t>(), s->W.raw_cam.as<int32_t>(),
+                                      s->W.pt_var_g.as<uint8_t>(), C, s->d_colq.as<int32_t>(), s->d_colt.as<int32_t>(), nt,
+                                      s->d_pat.as<uint8_t>(), st)))
+            return rc;
+        std::vector<uint8_t> pat((size_t)nt * nt);
+        XRB_CUDA(cudaMemcpyAsync(pat.data(), s->d_pat.p, pat.size(), cudaMemcpyDeviceToHost, st));
+        XRB_CUDA(cudaStreamSynchronize(st));
+        for (size_t v = 0; v < cam_of.size(); ++v) {  // a camera's own 6 x 6 block may straddle two tiles
+            const int t0 = start[v] >> 6, t1 = (start[v] + widths[v] - 1) >> 6;
+            pat[(size_t)t1 * nt + t0] = 1;
+        }
+        if ((rc = build_chol_plan(nt, pat.data(), s->plan.h))) {
+            set_error("ba_load: symbolic factorisation failed");
+            return rc;
+        }
+        if ((rc = s->plan.upload(st))) return rc;
+        lt.lap("plan (order + symbolic)");
+    }
 
     if ((rc = upload(s->d_intr, P->intr, 8 * (size_t)P->n_intr, st))) return rc;
     if ((rc = upload(s->d_intr_model, P->intr_model, (size_t)P->n_intr, st))) return rc;
@@ -218,11 +275,13 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
     }
     // ---- linear-system storage
     const int nc = s->nc;
-    s->tg = TileGeom::make(nc, s->bw);
-    const size_t nS = (size_t)s->tg.n_tiles() * 4096;
-    s->off_rhs = nS, s->off_U = s->off_rhs + (size_t)s->tg.nt * 64;
+    const int nt = s->plan.h.nt;
+    s->off_rhs = 0, s->off_U = s->off_rhs + (size_t)nt * 64;
     s->off_Ud = s->off_U + (size_t)nc * 6, s->off_gc = s->off_Ud + (size_t)nc * 6, s->off_scalE = s->off_gc + nc;
-    s->off_slots = s->off_scalE + SC_COUNT, s->off_n2c = s->off_slots + s->world;
+    s->off_slots = s->off_scalE + SC_COUNT;
+    s->off_S = (s->off_slots + s->world + 1) / 2 * 2;  // tiles stay 16-byte aligned
+    s->off_exch_end = s->off_S + (size_t)s->plan.h.n_tiles_orig * 4096;
+    s->off_n2c = s->off_S + (size_t)s->plan.h.n_tiles * 4096;
     s->E_count = s->off_n2c + nc;
     if ((rc = s->d_E.reserve(s->E_count * 8))) return rc;
     if ((rc = s->d_Vinv.reserve(std::max<size_t>(1, 6 * (size_t)s->P_local) * 8))) return rc;
@@ -231,7 +290,7 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
     if ((rc = s->d_step_p.reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
     if ((rc = s->d_sc.reserve(std::max<size_t>(1, nc) * 8))) return rc;
     if ((rc = s->d_yc.reserve(std::max<size_t>(1, nc) * 8))) return rc;
-    if ((rc = s->d_linv.reserve((size_t)(s->tg.nt + 1) * 4 * 256 * 8))) return rc;
+    if ((rc = s->d_linv.reserve((size_t)(nt + 1) * 4 * 256 * 8))) return rc;
     if ((rc = s->d_scal.reserve(2 * SC_COUNT * 8))) return rc;
     if (!s->h_scal) XRB_CUDA(cudaMallocHost(&s->h_scal, (3 * SC_COUNT + 64) * sizeof(double)));
     if (s->world > 64) {
@@ -276,11 +335,12 @@ int compute_step(xrb_ba_solver *s, const BAConsts &k, double radius, cudaStream_
     if (s->world > 1) {
         XRB_CUDA(cudaMemcpyAsync(s->slots() + s->rank, s->scalE() + SC_GRAD_MAX_PT, 8, cudaMemcpyDeviceToDevice, st));
         // S | U | gc | scalars | per-rank slots: ONE all-reduce per linear solve
-        if ((rc = s->exchange(s->d_E.as<double>(), s->off_n2c, st))) return rc;
+        if ((rc = s->exchange(s->d_E.as<double>(), s->off_exch_end, st))) return rc;
     }
     ev[2].rec(st);
+    if ((rc = ba_launch_set_holes(L, s->d_holes.as<int32_t>(), s->n_holes, st))) return rc;
     if ((rc = ba_launch_cam_diag(P, x, L, inv_radius, s->scalL(), st))) return rc;
-    if ((rc = ba_launch_tile_cholesky_solve(s->tg, L.S, L.rhs, s->d_linv.as<double>(), s->d_yc.as<double>(),
+    if ((rc = ba_launch_tile_cholesky_solve(s->plan.d, L.S, L.rhs, s->d_linv.as<double>(), s->d_yc.as<double>(),
                                             s->scalL() + SC_FAIL, st, &s->launches[1])))
         return rc;
     s->launches[1]++;
@@ -614,8 +674,9 @@ void xrb_ba_destroy(xrb_ba_solver *s) {
                       &s->d_obs_cam, &s->d_obs_uv, &s->d_pt_var, &s->d_obs_orig, &s->d_E, &s->d_Vinv, &s->d_gp,
                       &s->d_sc, &s->d_sp, &s->d_linv, &s->d_yc, &s->d_step_p, &s->d_scal, &s->d_full,
                       &s->d_obs_pt, &s->d_cam_ptr, &s->d_cam_obs, &s->d_inc, &s->d_blk_ptr, &s->d_blk_cams,
-                      &s->d_Tt, &s->d_h};
+                      &s->d_Tt, &s->d_h, &s->d_holes, &s->d_pat};
     for (DevBuf *b : bufs) b->release();
+    s->plan.release();
     s->W.release();
     for (int i = 0; i < 3; ++i) s->d_q[i].release(), s->d_t[i].release(), s->d_X[i].release();
     if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -744,24 +805,34 @@ int xrb_debug_chol_trace(int enable, int64_t *out, int cap_records) {
 }
 
 /* debug hook (not part of the reference surface): factor + solve one dense-stored SPD system with
- * the tile solver, on the current device */
+ * the tile solver, on the current device.  The tile pattern is taken from the non-zeros of A. */
 int xrb_debug_tile_solve(int n, int bw, const double *A, const double *rhs, double *x_out, int reps,
                          double *ms_out) {
     if (n <= 0 || !A || !rhs || !x_out || reps < 1) return XRB_ERR_INVALID;
     XRB_CUDA(cudaFree(0));
-    const TileGeom g = TileGeom::make(n, bw);
-    const size_t nS = (size_t)g.n_tiles() * 4096, nR = (size_t)g.nt * 64;
-    std::vector<double> packed(nS + nR, 0.0);
+    const int nt = (n + 63) / 64, np = nt * 64;
+    std::vector<uint8_t> pat((size_t)nt * nt, 0);
     for (int r = 0; r < n; ++r)
-        for (int c = std::max(0, r - bw); c <= r; ++c) packed[g.at(r, c)] = A[(size_t)r * n + c];
-    for (int r = 0; r < n; ++r) packed[nS + r] = rhs[r];
-    DevBuf E, dinv, x, fail;
-    int rc;
-    if ((rc = E.reserve(packed.size() * 8)) || (rc = dinv.reserve((size_t)(g.nt + 1) * 1024 * 8)) ||
-        (rc = x.reserve(nR * 8)) || (rc = fail.reserve(8)))
-        return rc;
+        for (int c = std::max(0, r - bw); c <= r; ++c)
+            if (A[(size_t)r * n + c] != 0.0) pat[(size_t)(r >> 6) * nt + (c >> 6)] = 1;
+    CholPlan plan;
+    int rc = build_chol_plan(nt, pat.data(), plan.h);
+    if (rc) return rc;
     cudaStream_t st;
     XRB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if ((rc = plan.upload(st))) return rc;
+    const size_t nS = (size_t)plan.h.n_tiles * 4096, nR = (size_t)np;
+    std::vector<double> packed(nS + nR, 0.0);
+    auto at = [&](int r, int c) { return (size_t)plan.h.tab[(size_t)(r >> 6) * nt + (c >> 6)] * 4096 + (size_t)((r & 63) * 64 + (c & 63)); };
+    for (int r = 0; r < n; ++r)
+        for (int c = std::max(0, r - bw); c <= r; ++c)
+            if (A[(size_t)r * n + c] != 0.0) packed[at(r, c)] = A[(size_t)r * n + c];
+    for (int r = n; r < np; ++r) packed[at(r, r)] = 1.0;
+    for (int r = 0; r < n; ++r) packed[nS + r] = rhs[r];
+    DevBuf E, dinv, x, fail;
+    if ((rc = E.reserve(packed.size() * 8)) || (rc = dinv.reserve((size_t)(nt + 1) * 1024 * 8)) ||
+        (rc = x.reserve(nR * 8)) || (rc = fail.reserve(8)))
+        return rc;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0), cudaEventCreate(&e1);
     float best = 1e30f;
@@ -770,7 +841,7 @@ int xrb_debug_tile_solve(int n, int bw, const double *A, const double *rhs, doub
         cudaMemsetAsync(fail.p, 0, 8, st);
         cudaMemsetAsync(x.p, 0, nR * 8, st);
         cudaEventRecord(e0, st);
-        rc = ba_launch_tile_cholesky_solve(g, E.as<double>(), E.as<double>() + nS, dinv.as<double>(), x.as<double>(),
+        rc = ba_launch_tile_cholesky_solve(plan.d, E.as<double>(), E.as<double>() + nS, dinv.as<double>(), x.as<double>(),
                                            fail.as<double>(), st, nullptr);
         cudaEventRecord(e1, st);
         if (cudaStreamSynchronize(st) != cudaSuccess) rc = XRB_ERR_CUDA;
@@ -792,15 +863,53 @@ int xrb_debug_tile_solve(int n, int bw, const double *A, const double *rhs, doub
     if (ms_out) *ms_out = best;
     cudaEventDestroy(e0), cudaEventDestroy(e1);
     cudaStreamDestroy(st);
-    E.release(), dinv.release(), x.release(), fail.release();
+    E.release(), dinv.release(), x.release(), fail.release(), plan.release();
     return rc;
+}
+
+/* debug hooks, host only (no device needed): the symbolic plan of a tile pattern and the column order.
+ * counts[16] = nt, n_tiles, n_tiles_orig, n_f, n_w, n_b, n_wb, n_far, n_chain_f, n_chain_b, depth_f, depth_b.
+ * Output arrays may be null; each is filled up to its capacity (in int32 elements). */
+int xrb_debug_chol_plan(int nt, const uint8_t *pat, int32_t *counts, int32_t *tab, int32_t *ftasks, int cap_f,
+                        int32_t *wtasks, int cap_w, int32_t *btasks, int cap_b, int32_t *wbtasks, int cap_wb,
+                        int32_t *far_rows, int32_t *far_slots, int cap_far) {
+    if (nt <= 0 || !pat || !counts) return XRB_ERR_INVALID;
+    CholPlanHost H;
+    const int rc = build_chol_plan(nt, pat, H);
+    if (rc) return rc;
+    const int32_t c[16] = {H.nt, H.n_tiles, H.n_tiles_orig, H.n_f, H.n_w, H.n_b, H.n_wb, (int32_t)H.far_rows.size(),
+                           H.n_chain_f, H.n_chain_b, H.depth_f, H.depth_b, 0, 0, 0, 0};
+    memcpy(counts, c, sizeof c);
+    auto copy = [](int32_t *dst, int cap, const std::vector<int32_t> &v) {
+        if (dst && cap > 0 && !v.empty()) memcpy(dst, v.data(), std::min<size_t>(cap, v.size()) * 4);
+    };
+    copy(tab, nt * nt, H.tab), copy(ftasks, cap_f, H.ftasks), copy(wtasks, cap_w, H.wtasks), copy(btasks, cap_b, H.btasks);
+    copy(wbtasks, cap_wb, H.wbtasks), copy(far_rows, cap_far, H.far_rows), copy(far_slots, cap_far, H.far_slots);
+    return XRB_OK;
+}
+
+int xrb_debug_column_order(int n_cams, const int32_t *widths, int bw, int allow_nd, int32_t *start, int32_t *n_pad,
+                           int32_t *parts) {
+    if (n_cams < 0 || (n_cams && (!widths || !start)) || !n_pad || !parts) return XRB_ERR_INVALID;
+    std::vector<int> w(widths, widths + n_cams);
+    std::vector<int32_t> st;
+    int np = 0, pa = 1;
+    plan_column_order(w, bw, allow_nd != 0, st, np, pa);
+    for (int v = 0; v < n_cams; ++v) start[v] = st[v];
+    *n_pad = np, *parts = pa;
+    return XRB_OK;
 }
 
 int xrb_ba_profile_detail(const xrb_ba_solver *s, double *out, int n) {
     if (!s || !out || n < 8) return XRB_ERR_INVALID;
     out[0] = s->ms_kernel[0], out[1] = s->ms_kernel[1], out[2] = s->ms_kernel[2];
     out[3] = (double)s->n_steps, out[4] = (double)s->n_blocks, out[5] = (double)s->n_inc;
-    out[6] = (double)s->nc, out[7] = (double)s->bw;
+    out[6] = (double)s->nc_true, out[7] = (double)s->bw;
+    if (n >= 16) {
+        const CholPlanHost &h = s->plan.h;
+        out[8] = s->parts, out[9] = h.nt, out[10] = h.n_tiles, out[11] = h.n_tiles_orig, out[12] = h.flops;
+        out[13] = h.depth_f, out[14] = h.depth_b, out[15] = h.n_chain_f;
+    }
     return XRB_OK;
 }
 

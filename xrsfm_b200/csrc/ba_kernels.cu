@@ -488,9 +488,9 @@ k_gather(BAProblemDev P, BALinSys L) {
         if (ra[a] < 0 || cb[c] < 0) continue;
         if (same) {
             if (c > a) continue;
-            L.S[L.tg.at(ra[a], cb[c])] = -(acc[a * 6 + c] + acc[c * 6 + a]);
+            L.S[L.tm.at(ra[a], cb[c])] = -(acc[a * 6 + c] + acc[c * 6 + a]);
         } else {
-            L.S[L.tg.at(ra[a], cb[c])] = -acc[e];
+            L.S[L.tm.at(ra[a], cb[c])] = -acc[e];
         }
     }
 }
@@ -603,7 +603,7 @@ __global__ void k_cam_diag(BAProblemDev P, BAStateDev x, BALinSys L, double inv_
             if (cols[b] < 0) continue;
             double v = L.U[(size_t)cols[a] * 6 + b];
             if (a == b) v += fmin(fmax(v, 1e-6), 1e32) * inv_radius;
-            L.S[L.tg.at(cols[a], cols[b])] += v - L.Ud[(size_t)cols[a] * 6 + b];
+            L.S[L.tm.at(cols[a], cols[b])] += v - L.Ud[(size_t)cols[a] * 6 + b];
         }
     }
     double gmax = 0.0;
@@ -624,6 +624,20 @@ int ba_launch_cam_diag(const BAProblemDev &P, const BAStateDev &x, const BALinSy
                        double inv_radius, double *scalars, cudaStream_t st) {
     k_cam_diag<<<(P.n_cams + 127) / 128, 128, 0, st>>>(P, x, L, inv_radius, scalars);
     XRB_LAUNCHED();
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+__global__ void k_set_holes(BALinSys L, const int32_t *__restrict__ holes, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) L.S[L.tm.at(holes[i], holes[i])] = 1.0;
+}
+
+int ba_launch_set_holes(const BALinSys &L, const int32_t *holes, int n_holes, cudaStream_t st) {
+    if (n_holes > 0) {
+        k_set_holes<<<(n_holes + 255) / 256, 256, 0, st>>>(L, holes, n_holes);
+        XRB_LAUNCHED();
+    }
     XRB_CUDA(cudaGetLastError());
     return XRB_OK;
 }

@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <vector>
 
+#include "ba_plan.cuh"
 #include "common.cuh"
 
 namespace xrb {
@@ -50,44 +51,17 @@ struct BAStateDev {
     double *q, *t, *X;  // [4C], [3C], [3 * n_pts_local]
 };
 
-// Tile-major storage of the lower triangle of the reduced camera system S (n x n, half bandwidth
-// bw): 64 x 64 tiles, each one contiguous row-major 32 KB block, ordered tile-column by tile-column,
-// only the tiles (i, j) with 0 <= i - j < h (h - 1 = the half bandwidth in tiles).  A block column
-// is one contiguous range; a dense system stores nt (nt + 1) / 2 tiles, a banded one about nt * h.
-struct TileGeom {
-    int n = 0, nt = 0, h = 1, J0 = 0;  // J0 = nt - h: first tile column whose height is cut by the matrix end
-    __host__ __device__ static TileGeom make(int n_, int bw) {
-        TileGeom g;
-        g.n = n_, g.nt = (n_ + 63) / 64;
-        const int bwt = (bw + 63) / 64;  // tiles below the diagonal that element distance bw can reach
-        g.h = g.nt < bwt + 1 ? (g.nt > 0 ? g.nt : 1) : bwt + 1;
-        g.J0 = g.nt - g.h;
-        return g;
-    }
-    __host__ __device__ int colstart(int j) const {
-        int m = j - 1 - J0;
-        m = m > 0 ? m : 0;
-        return j * h - m * (m + 1) / 2;
-    }
-    __host__ __device__ int n_tiles() const { return colstart(nt); }
-    __host__ __device__ int tile(int i, int j) const { return colstart(j) + (i - j); }
-    __host__ __device__ int first_col(int i) const { return i - (h - 1) > 0 ? i - (h - 1) : 0; }
-    // element (r, c), r >= c, r - c <= bw
-    __host__ __device__ size_t at(int r, int c) const {
-        return (size_t)tile(r >> 6, c >> 6) * 4096 + (size_t)((r & 63) * 64 + (c & 63));
-    }
-};
-
 // Exchange buffer layout (one SUM all-reduce per linear solve in multi-GPU mode):
-//   S    : n_tiles x 4096  tile-major lower triangle of the reduced camera system (TileGeom)
 //   rhs  : nt x 64         right-hand side (padded); becomes y = L^-1 rhs during the factorisation
 //   U    : nc x 6          rows of the camera block-diagonal J_c^T J_c
 //   Ud   : nc x 6          rows of the diagonal blocks of W V^-1 W^T (subtracted by k_cam_diag)
 //   gc   : nc              J_c^T r (scaled), for the gradient norm
-//   n2c  : nc              squared column norms (iteration 0 only)
+//   S    : n_tiles_orig x 4096  the structurally non-zero tiles of the lower triangle (TileMap);
+//                          the fill tiles follow and are not exchanged
+//   n2c  : nc              squared column norms (iteration 0 only, exchanged on its own)
 struct BALinSys {
     double *S;
-    TileGeom tg;
+    TileMap tm;
     double *rhs;
     double *U, *Ud, *gc, *n2c;
     double *Vinv, *gp;  // per local point: V^-1 (6), g_p (3)
@@ -133,11 +107,13 @@ int ba_launch_cost(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k
 int ba_launch_residuals(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
                         const int32_t *obs_orig, double *out, cudaStream_t st);
 
-// ba_tilechol.cu — Cholesky of the tile-major S in one persistent kernel (tile DAG over resident
-// CTAs, flags in global memory), forward substitution folded in (rhs -> y), back-substitution in a
-// second kernel.  dinv: nt x 4 x 256 doubles (inverses of the 16 x 16 diagonal blocks of L).
-int ba_launch_tile_cholesky_solve(const TileGeom &g, double *tiles, double *rhs, double *dinv, double *x_out,
+// ba_tilechol.cu — sparse tile Cholesky of S in one persistent kernel (task DAG over resident CTAs,
+// flags in global memory), forward substitution folded in (rhs -> y), back-substitution in a second
+// kernel.  dinv: nt x 4 x 256 doubles (inverses of the 16 x 16 diagonal blocks of L).
+int ba_launch_tile_cholesky_solve(const CholPlanDev &plan, double *tiles, double *rhs, double *dinv, double *x_out,
                                   double *fail_flag, cudaStream_t st, int64_t *launches);
+// identity rows of the padding columns (tile-aligned parts, matrix end): S[c][c] = 1 for the listed columns
+int ba_launch_set_holes(const BALinSys &L, const int32_t *holes, int n_holes, cudaStream_t st);
 int ba_tile_cholesky_aborted(int *aborted);
 // debug: clock64 of the chain CTA after each block column of the last factorisation
 int ba_tile_cholesky_trace(int enable, long long *out, int cap);

@@ -179,6 +179,7 @@ int ba_build_structure(const xrb_ba_problem *P, int rank, int world, BAStructScr
     if ((rc = out.colt->reserve(colt.size() * 4))) return rc;
     XRB_CUDA(cudaMemcpyAsync(out.colq->p, colq.data(), colq.size() * 4, cudaMemcpyHostToDevice, st));
     XRB_CUDA(cudaMemcpyAsync(out.colt->p, colt.data(), colt.size() * 4, cudaMemcpyHostToDevice, st));
+    info->h_colq = colq, info->h_colt = colt;
     k_point_struct<<<blocks_for(NP, 128), 128, 0, st>>>(NP, W.pt_ptr_g.as<int32_t>(), W.vals.as<int32_t>(),
                                                         W.raw_cam.as<int32_t>(), has_fixed ? W.pt_fixed.as<uint8_t>() : nullptr,
                                                         out.colq->as<int32_t>(), out.colt->as<int32_t>(),

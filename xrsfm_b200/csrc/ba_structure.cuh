@@ -67,6 +67,7 @@ struct BAStructInfo {
     int nc, n_var_q, n_var_t, n_var_pts, n_res_blocks, bw;
     int p_lo, P_local, O_local;
     std::vector<int32_t> shard_lo;  // [world + 1]: rank r owns points [shard_lo[r], shard_lo[r+1])
+    std::vector<int32_t> h_colq, h_colt;  // natural-order reduced columns (host copy; xrb_ba_load reorders them)
 };
 
 // Upload obs_cam/obs_pt/obs_uv and derive the structure for points [p_lo, p_hi) of this rank.
