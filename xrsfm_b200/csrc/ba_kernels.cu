@@ -435,12 +435,13 @@ __device__ __forceinline__ void load_rec(const double *__restrict__ Tt, int o, d
     }
 }
 
-constexpr int kLanesPerBlock = 8;
-
+// LPB lanes share one block: 8 for the short lists of an unordered scene (C2: ~70 incidences per block),
+// a whole warp for the long lists of a sequential one (C4: ~1900 per block, few blocks).
+template <int LPB>
 __global__ void __launch_bounds__(256)
 k_gather(BAProblemDev P, BALinSys L) {
-    const int sub = threadIdx.x & (kLanesPerBlock - 1);
-    const int b = (blockIdx.x * blockDim.x + threadIdx.x) / kLanesPerBlock;
+    const int sub = threadIdx.x & (LPB - 1);
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) / LPB;
     const bool live = b < P.n_blocks;
     double acc[36];
 #pragma unroll
@@ -450,9 +451,9 @@ k_gather(BAProblemDev P, BALinSys L) {
         // the index pair of the next incidence is requested before the records of this one:
         // index -> record is a dependent load chain, one L2 round trip per link
         int2 nxt = i0 + sub < i1 ? __ldg(P.inc + i0 + sub) : make_int2(0, 0);
-        for (int it = i0 + sub; it < i1; it += kLanesPerBlock) {
+        for (int it = i0 + sub; it < i1; it += LPB) {
             const int2 oo = nxt;
-            if (it + kLanesPerBlock < i1) nxt = __ldg(P.inc + it + kLanesPerBlock);
+            if (it + LPB < i1) nxt = __ldg(P.inc + it + LPB);
             double Ti[18], Tj[18];
             load_rec(L.Tt, oo.x, Ti);
             load_rec(L.Tt, oo.y, Tj);
@@ -466,9 +467,8 @@ k_gather(BAProblemDev P, BALinSys L) {
 #pragma unroll
     for (int j = 0; j < 36; ++j) {
         double v = acc[j];
-        v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
-        v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
-        v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+#pragma unroll
+        for (int d = 1; d < LPB; d <<= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
         acc[j] = v;
     }
     if (!live) return;
@@ -480,10 +480,10 @@ k_gather(BAProblemDev P, BALinSys L) {
         cb[j] = P.colq[cams.y] >= 0 ? P.colq[cams.y] + j : -1, cb[3 + j] = P.colt[cams.y] >= 0 ? P.colt[cams.y] + j : -1;
     }
     const bool same = cams.x == cams.y;  // two observations of one camera on one point: M + M^T
-    // the 8 lanes of the group share the 36 stores
+    // the lanes of the group share the 36 stores
 #pragma unroll
     for (int e = 0; e < 36; ++e) {
-        if ((e & (kLanesPerBlock - 1)) != sub) continue;
+        if ((e & (LPB - 1)) != sub) continue;
         const int a = e / 6, c = e % 6;
         if (ra[a] < 0 || cb[c] < 0) continue;
         if (same) {
@@ -497,8 +497,13 @@ k_gather(BAProblemDev P, BALinSys L) {
 
 int ba_launch_gather(const BAProblemDev &P, const BALinSys &L, cudaStream_t st) {
     if (P.n_blocks > 0) {
-        const long long threads = (long long)P.n_blocks * kLanesPerBlock;
-        k_gather<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, L);
+        if (P.n_inc > 256LL * P.n_blocks) {
+            const long long threads = (long long)P.n_blocks * 32;
+            k_gather<32><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, L);
+        } else {
+            const long long threads = (long long)P.n_blocks * 8;
+            k_gather<8><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, L);
+        }
         XRB_LAUNCHED();
     }
     XRB_CUDA(cudaGetLastError());

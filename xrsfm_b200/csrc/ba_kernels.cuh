@@ -41,6 +41,7 @@ struct BAProblemDev {
     const int32_t *obs_pt;                      // [n_obs_local] local point of each observation
     const int32_t *cam_ptr, *cam_obs;           // camera-major CSR of point-major obs indices
     int n_blocks;                               // off-diagonal 6x6 blocks of S with >= 1 point
+    long long n_inc;                            // (block, point) incidences in `inc`
     const int32_t *blk_ptr;                     // [n_blocks + 1] offsets into inc
     const int2 *blk_cams;                       // [n_blocks] (cam_a, cam_b), cols(a) >= cols(b)
     const int2 *inc;                            // (obs_i of cam_a, obs_j of cam_b), same point
