@@ -253,6 +253,21 @@ int xrb_ba_fetch(xrb_ba_solver *s, xrb_ba_problem *prob);
  * ReProjectionCost::operator() (cost_factor_ceres.h:19-40) over the whole problem. */
 int xrb_ba_residuals(xrb_ba_solver *s, double *out_residuals);
 
+/* Post-BA point filter on the solver's CURRENT state (after xrb_ba_run / xrb_ba_solve; single GPU).
+ * Replaces Point3dProcessor::FilterPoints3d(map, max_re, deg) (src/geometry/track_processor.cc:321-349,
+ * FilterPoint3d :279-319, UpdateTrackAngle :253-277, Reprojection_Error :19-26), which the mapper calls
+ * after every KGBA (src/mapper/incremental_mapper.cc:83-85) — the poses and points it needs are still
+ * resident.  HOST outputs, indexed like the loaded problem:
+ *   keep_obs[n_obs]    0 = the reference would DeleteObservation / drop it with its track
+ *   pt_outlier[n_pts]  1 = SetTrackOutlier
+ *   pt_error[n_pts]    track.error (mean reprojection error of the kept observations), 0 if not computed
+ *   pt_angle[n_pts]    track.angle_ as the early-exit scan leaves it (radians), 0 if not computed
+ *   counts[2]          num_filtered1 (observations), num_filtered2 (tracks by angle)
+ * A track's observations are visited in ascending camera index (the reference iterates a std::map keyed
+ * by frame id: flatten the frames in id order, as the BA flattening does). */
+int xrb_ba_filter_points3d(xrb_ba_solver *s, double max_re, double deg, uint8_t *keep_obs, uint8_t *pt_outlier,
+                           double *pt_error, double *pt_angle, int32_t counts[2]);
+
 /* Last-run device timings in milliseconds: [0] linearise+Schur, [1] reduced system
  * factor+solve, [2] back-substitution+update, [3] cost evaluation, [4] exchange,
  * [5] whole run; and launches of each (same indices). */

@@ -315,3 +315,52 @@ def test_c4_shaped_scene_dissected_order(solver, monkeypatch):
         assert a.step_is_successful == b.step_is_successful, i
         assert a.cost == pytest.approx(b.cost, rel=1e-6 if i <= 4 else 1e-4), i
     assert np.abs(got.cam_q - nat.cam_q).max() < 1e-3
+
+
+def _oracle_filter(sc, max_re, deg):
+    import ctypes as C
+    h = ol.load()
+    h.xro_filter_points3d.restype = C.c_int
+    h.xro_filter_points3d.argtypes = [C.c_void_p, C.c_double, C.c_double] + [C.c_void_p] * 5
+    prob = ol.ba_problem(sc)
+    keep = np.zeros(sc.n_obs, dtype=np.uint8)
+    outl = np.zeros(sc.n_pts, dtype=np.uint8)
+    err, ang = np.zeros(sc.n_pts), np.zeros(sc.n_pts)
+    cnt = np.zeros(2, dtype=np.int32)
+    assert h.xro_filter_points3d(C.byref(prob), max_re, deg, keep.ctypes.data, outl.ctypes.data, err.ctypes.data,
+                                 ang.ctypes.data, cnt.ctypes.data) == 0
+    return keep, outl, err, ang, (int(cnt[0]), int(cnt[1]))
+
+
+@pytest.mark.parametrize("scene,max_re,deg", [("C1", 8.0, 2.0), ("C1", 2.0, 0.5), ("seq", 8.0, 2.0), ("shuffled", 4.0, 1.0)])
+def test_filter_points3d_equals_oracle(solver, scene, max_re, deg):
+    """FilterPoints3d (track_processor.cc:321-349) on the resident state: deleted observations, outlier
+    tracks and both counters bit-exact against the oracle; track error / angle to round-off."""
+    if scene == "C1":
+        sc = synth.make_scene("C1")
+        sc.pts[int(sc.obs_pt[0])] *= 400.0             # a far point: tiny triangulation angle
+    elif scene == "seq":
+        sc = synth.make_sequential_scene(60, 3000, 7, 17)
+    else:                                              # observations of a point not in camera order
+        sc = synth.make_sphere_scene(25, 1500, 9, 19)
+        perm = np.random.default_rng(3).permutation(sc.n_obs)
+        sc["obs_cam"], sc["obs_pt"] = np.ascontiguousarray(sc.obs_cam[perm]), np.ascontiguousarray(sc.obs_pt[perm])
+        sc["obs_uv"] = np.ascontiguousarray(sc.obs_uv[perm])
+    solver.load(sc)
+    keep, outl, err, ang, cnt = solver.filter_points3d(max_re, deg)
+    k2, o2, e2, a2, c2 = _oracle_filter(sc, max_re, deg)
+    np.testing.assert_array_equal(keep, k2)
+    np.testing.assert_array_equal(outl, o2)
+    assert cnt == c2
+    first_ok = e2 > 0
+    np.testing.assert_allclose(err[first_ok], e2[first_ok], rtol=1e-12)
+    np.testing.assert_allclose(ang[first_ok], a2[first_ok], rtol=1e-9, atol=1e-13)
+    assert 0 < outl.sum() < sc.n_pts and 0 < keep.sum() < sc.n_obs
+    # after a solve the filter sees the optimised state
+    s = solver.run(**ol.GBA_FAST)
+    solver.fetch()
+    keep3, outl3, _, _, cnt3 = solver.filter_points3d(max_re, deg)
+    k4, o4, _, _, c4 = _oracle_filter(sc, max_re, deg)  # sc now holds the fetched state
+    np.testing.assert_array_equal(keep3, k4)
+    np.testing.assert_array_equal(outl3, o4)
+    assert cnt3 == c4 and s.num_lm_iterations > 0

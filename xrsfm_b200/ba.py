@@ -152,6 +152,20 @@ class BASolver:
         names = ("schur", "solve", "backsub", "cost", "exchange", "run")
         return {n: (ms[i], ln[i]) for i, n in enumerate(names)}
 
+    def filter_points3d(self, max_re, deg):
+        """Point3dProcessor::FilterPoints3d (track_processor.cc:321-349) on the solver's current state.
+        Returns (keep_obs, pt_outlier, pt_error, pt_angle, (num_filtered1, num_filtered2))."""
+        n_obs, n_pts = int(self._problem.n_obs), int(self._problem.n_pts)
+        keep = np.zeros(max(1, n_obs), dtype=np.uint8)
+        out = np.zeros(max(1, n_pts), dtype=np.uint8)
+        err = np.zeros(max(1, n_pts))
+        ang = np.zeros(max(1, n_pts))
+        counts = np.zeros(2, dtype=np.int32)
+        _lib.check(_lib.lib().xrb_ba_filter_points3d(self._h, float(max_re), float(deg), keep.ctypes.data, out.ctypes.data,
+                                                     err.ctypes.data, ang.ctypes.data, counts.ctypes.data),
+                   "xrb_ba_filter_points3d")
+        return keep[:n_obs], out[:n_pts], err[:n_pts], ang[:n_pts], (int(counts[0]), int(counts[1]))
+
     def profile_detail(self):
         out = (C.c_double * 16)()
         _lib.check(_lib.lib().xrb_ba_profile_detail(self._h, out, 16), "xrb_ba_profile_detail")

@@ -798,6 +798,45 @@ int xrb_ba_residuals(xrb_ba_solver *s, double *out) {
     return rc;
 }
 
+/* Post-BA filter on the solver's current state (single GPU): see include/xrsfm_b200.h */
+int xrb_ba_filter_points3d(xrb_ba_solver *s, double max_re, double deg, uint8_t *keep_obs, uint8_t *pt_outlier,
+                           double *pt_error, double *pt_angle, int32_t counts[2]) {
+    if (!s || !s->loaded || !keep_obs || !pt_outlier || !pt_error || !pt_angle || !counts) return XRB_ERR_INVALID;
+    XRB_CUDA(cudaSetDevice(s->device));
+    if (s->world > 1) {
+        set_error("ba_filter_points3d: single-GPU only");
+        return XRB_ERR_INVALID;
+    }
+    cudaStream_t st = s->own_stream;
+    const size_t NO = (size_t)s->O_total, NP = (size_t)s->P_total;
+    DevBuf tmp;
+    const size_t o_ctr = 0, o_err = o_ctr + 24 * (size_t)std::max(1, s->C), o_ang = o_err + 8 * std::max<size_t>(1, NP);
+    const size_t o_order = o_ang + 8 * std::max<size_t>(1, NP), o_cnt = o_order + 4 * std::max<size_t>(1, NO);
+    const size_t o_flag = o_cnt + 16, o_keep = o_flag + std::max<size_t>(1, NO), o_out = o_keep + std::max<size_t>(1, NO);
+    int rc = tmp.reserve(o_out + std::max<size_t>(1, NP));
+    if (rc) return rc;
+    char *b = tmp.as<char>();
+    rc = ba_launch_filter(s->prob(), s->state(s->cur), s->d_obs_orig.as<int32_t>(), reinterpret_cast<double *>(b + o_ctr),
+                          reinterpret_cast<int32_t *>(b + o_order), reinterpret_cast<uint8_t *>(b + o_flag), max_re, deg,
+                          reinterpret_cast<uint8_t *>(b + o_keep), reinterpret_cast<uint8_t *>(b + o_out),
+                          reinterpret_cast<double *>(b + o_err), reinterpret_cast<double *>(b + o_ang),
+                          reinterpret_cast<int32_t *>(b + o_cnt), st);
+    if (rc == XRB_OK) {
+        bool ok = true;
+        if (NO) ok &= cudaMemcpyAsync(keep_obs, b + o_keep, NO, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        if (NP) {
+            ok &= cudaMemcpyAsync(pt_outlier, b + o_out, NP, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            ok &= cudaMemcpyAsync(pt_error, b + o_err, NP * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            ok &= cudaMemcpyAsync(pt_angle, b + o_ang, NP * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        }
+        ok &= cudaMemcpyAsync(counts, b + o_cnt, 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        if (!ok) rc = XRB_ERR_CUDA;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = XRB_ERR_CUDA;
+    tmp.release();
+    return rc;
+}
+
 /* debug hook (not part of the reference surface): timeline of the Cholesky kernels */
 int xrb_debug_chol_trace(int enable, int64_t *out, int cap_records) {
     static_assert(sizeof(long long) == sizeof(int64_t), "");

@@ -108,6 +108,11 @@ int ba_launch_cost(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k
 int ba_launch_residuals(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
                         const int32_t *obs_orig, double *out, cudaStream_t st);
 
+// ba_filter.cu — post-BA point filter (FilterPoints3d, track_processor.cc:321-349) over the resident CSR
+int ba_launch_filter(const BAProblemDev &P, const BAStateDev &st, const int32_t *obs_orig, double *ctr, int32_t *order,
+                     uint8_t *flag, double max_re, double deg, uint8_t *keep_obs, uint8_t *pt_outlier, double *pt_error,
+                     double *pt_angle, int32_t *counts, cudaStream_t stream);
+
 // ba_tilechol.cu — sparse tile Cholesky of S in one persistent kernel (task DAG over resident CTAs,
 // flags in global memory), forward substitution folded in (rhs -> y), back-substitution in a second
 // kernel.  dinv: nt x 4 x 256 doubles (inverses of the 16 x 16 diagonal blocks of L).

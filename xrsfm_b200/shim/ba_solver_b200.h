@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cmath>
+#include <map>
 #include <unordered_map>
 #include <set>
 #include <vector>
@@ -113,14 +114,17 @@ inline void PrintSolverSummary(const xrb_ba_summary &s) {
                 "Termination : ", s.termination_type >= 0 && s.termination_type <= 2 ? term[s.termination_type] : "Unknown");
 }
 
+// One engine per device, created on first use (a handle owns its streams and buffers).
 inline xrb_ba_solver *Engine(int device = 0) {
-    static xrb_ba_solver *h = xrb_ba_create(device);
-    return h;
+    static std::map<int, xrb_ba_solver *> engines;
+    auto it = engines.find(device);
+    if (it == engines.end()) it = engines.emplace(device, xrb_ba_create(device)).first;
+    return it->second;
 }
 
 // Body of BASolver::GBA (ba_solver.cc:594-638).
 template <class MapT>
-int GBA(MapT &map, bool accurate = true, bool fix_all_frames = false) {
+int GBA(MapT &map, bool accurate = true, bool fix_all_frames = false, int device = 0) {
     FlatBA f = Flatten(map, /*keyframes_only=*/false, fix_all_frames);
     xrb_ba_options o;
     xrb_ba_default_options(&o);
@@ -130,7 +134,7 @@ int GBA(MapT &map, bool accurate = true, bool fix_all_frames = false) {
     o.parameter_tolerance = accurate ? 1e-6 : 1e-5;
     xrb_ba_problem p = f.problem();
     xrb_ba_summary s;
-    const int rc = xrb_ba_solve(Engine(), &p, &o, &s);
+    const int rc = xrb_ba_solve(Engine(device), &p, &o, &s);
     if (rc != XRB_OK) {
         std::fprintf(stderr, "xrb_ba_solve failed (%d): %s\n", rc, xrb_last_error());
         return rc;
@@ -143,7 +147,7 @@ int GBA(MapT &map, bool accurate = true, bool fix_all_frames = false) {
 // Solver part of BASolver::KGBA (ba_solver.cc:645-675); the caller keeps
 // KeyFrameSelection(map, ...) before and UpdateByRefFrame(map) after (:641,:677).
 template <class MapT>
-int KGBA_Solve(MapT &map) {
+int KGBA_Solve(MapT &map, int device = 0) {
     FlatBA f = Flatten(map, /*keyframes_only=*/true, false);
     xrb_ba_options o;
     xrb_ba_default_options(&o);
@@ -151,7 +155,7 @@ int KGBA_Solve(MapT &map) {
     o.initial_radius = 1e6, o.max_iterations = 20, o.function_tolerance = 1e-4, o.parameter_tolerance = 1e-5;
     xrb_ba_problem p = f.problem();
     xrb_ba_summary s;
-    const int rc = xrb_ba_solve(Engine(), &p, &o, &s);
+    const int rc = xrb_ba_solve(Engine(device), &p, &o, &s);
     if (rc != XRB_OK) {
         std::fprintf(stderr, "xrb_ba_solve failed (%d): %s\n", rc, xrb_last_error());
         return rc;
@@ -232,14 +236,14 @@ FlatBA FlattenLBA(MapT &map, int frame_id, const std::vector<int> &local_frame_i
 // Solver part of BASolver::LBA (ba_solver.cc:586-591): 5 iterations, 1e-4 / 1e-5, no summary print.
 template <class MapT>
 int LBA_Solve(MapT &map, int frame_id, const std::vector<int> &local_frame_ids1,
-              const std::vector<int> &local_frame_ids2) {
+              const std::vector<int> &local_frame_ids2, int device = 0) {
     FlatBA f = FlattenLBA(map, frame_id, local_frame_ids1, local_frame_ids2);
     xrb_ba_options o;
     xrb_ba_default_options(&o);
     o.max_iterations = 5, o.function_tolerance = 1e-4, o.parameter_tolerance = 1e-5;
     xrb_ba_problem p = f.problem();
     xrb_ba_summary s;
-    const int rc = xrb_ba_solve(Engine(), &p, &o, &s);
+    const int rc = xrb_ba_solve(Engine(device), &p, &o, &s);
     if (rc != XRB_OK) {
         std::fprintf(stderr, "xrb_ba_solve failed (%d): %s\n", rc, xrb_last_error());
         return rc;
@@ -247,5 +251,55 @@ int LBA_Solve(MapT &map, int frame_id, const std::vector<int> &local_frame_ids1,
     Scatter(f, map);
     return rc;
 }
+
+// class BASolver of src/optimization/ba_solver.h:14-30 with the same four public methods.  The map
+// walks that are not bundle adjustment stay what they are in the reference and are found by
+// argument-dependent lookup in MapT's namespace (namespace xrsfm in the reference build):
+//   KeyFrameSelection(map, ids, is_sequential)  UpdateByRefFrame(map)      src/base/map.h:213-216
+//   CovisibilityNeibors(frame_id, map)  FindLocalBundle(frame_id, map)     ba_solver.cc:393-521
+//   ScalePoseGraphUnorder                                                  ba_solver.cc:79-328 (pose graph,
+//       Ceres on the host: SURVEY.md row B14 keeps it on the reference; `pose_graph` forwards to it)
+template <class MapT, class LoopInfoT = int>
+class BASolverT {
+  public:
+    explicit BASolverT(int device = 0) : device_(device) {}
+
+    void (*pose_graph)(const LoopInfoT &, MapT &, bool) = nullptr;
+    void ScalePoseGraphUnorder(const LoopInfoT &loop_info, MapT &map, bool use_key = false) {
+        if (pose_graph)
+            pose_graph(loop_info, map, use_key);
+        else
+            std::fprintf(stderr, "ScalePoseGraphUnorder: not part of the B200 path, set BASolverT::pose_graph\n");
+    }
+    void KGBA(MapT &map, const std::vector<int> fix_key_frame_ids, const bool is_sequential_data) {
+        KeyFrameSelection(map, fix_key_frame_ids, is_sequential_data);  // ba_solver.cc:641
+        int num_rf = 0, num_kf = 0;
+        for (auto &frame : map.frames_) {
+            if (!frame.registered) continue;
+            num_rf++;
+            num_kf += frame.is_keyframe ? 1 : 0;
+        }
+        last_status = KGBA_Solve(map, device_);
+        std::printf("kf: %d/%d\n", num_kf, num_rf);  // :676
+        UpdateByRefFrame(map);                       // :677
+    }
+    void GBA(MapT &map, bool accurate = true, bool fix_all_frames = false) {
+        last_status = xrsfm_b200::GBA(map, accurate, fix_all_frames, device_);
+    }
+    void LBA(int frame_id, MapT &map) {
+        const std::vector<int> ids1 = CovisibilityNeibors(frame_id, map);  // ba_solver.cc:525
+        const std::vector<int> ids2 = FindLocalBundle(frame_id, map);      // :526
+        std::set<int> local(ids1.begin(), ids1.end());
+        local.insert(ids2.begin(), ids2.end());
+        std::printf("LBA: ");
+        for (const int id : local) std::printf(" %d", id);
+        std::printf("\n");
+        last_status = LBA_Solve(map, frame_id, ids1, ids2, device_);
+    }
+    int last_status = XRB_OK;
+
+  private:
+    int device_;
+};
 
 }  // namespace xrsfm_b200
