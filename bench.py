@@ -352,13 +352,20 @@ def ba_rooflines(out):
     gat_b = ba_gather_unique_bytes(detail, sc.n_obs)
     gat_ach = gat_b / (kern_ms["k_gather"] * 1e-3) / 1e9
     it_b = ba_iteration_bytes(sc, detail)
-    roof = {"kernel": "k_tile_cholesky + k_tile_backsolve (persistent tile-DAG Cholesky of the reduced camera system)",
-            "bound": "fp64 FMA pipe (a dense contraction in FP64: neither HBM nor the low-precision tensor pipe)",
-            "achieved": chol_tf, "peak": dfma, "peak_source": fsrc, "unit": "TFLOP/s", "frac": chol_tf / dfma,
+    roof = {"kernel": "k_tile_cholesky + k_tile_backsolve (sparse tile Cholesky of the reduced camera system: task DAG "
+                      "over resident CTAs, tile products on the FP64 tensor pipe)",
+            "bound": "tensor", "bound_note": "FP64 tensor pipe (mma.sync.m8n8k4.f64, DMMA) for the tile products; the "
+                                             "diagonal chain (POTRF of 64 x 64 tiles) is dependency-latency bound",
+            "achieved": chol_tf, "peak": dmma, "peak_source": fsrc, "unit": "TFLOP/s", "frac": chol_tf / dmma,
             "share_of_step": chol_ms / step_ms, "ms_per_launch": chol_ms, "traffic": None,
             "algorithmic_flops_per_launch": ba_chol_flops(detail["nc"], detail["half_bandwidth"]),
-            "tensor_pipe_note": f"FP64 tensor (DMMA m8n8k4) peak measured at {dmma:.1f} TFLOP/s vs {dfma:.1f} for DFMA on this "
-                                "part; the kernel issues DFMA"}
+            "executed_flops_per_launch": detail["plan_flops"],
+            "plan": {"column_order_parts": int(detail["parts"]), "tile_columns": int(detail["tile_columns"]),
+                     "tiles": int(detail["tiles"]), "tiles_original": int(detail["tiles_original"]),
+                     "longest_dependency_path_tasks": int(detail["depth_factor"]), "chains": int(detail["chains"])},
+            "tensor_pipe_note": f"FP64 tensor (DMMA m8n8k4) peak measured at {dmma:.1f} TFLOP/s, DFMA {dfma:.1f} on this part; "
+                                "algorithmic flops = n^3/3 (dense) or n bw^2 (band) + substitutions, the fill of a "
+                                "dissected band is not counted"}
     out["roofline"] = roof
     out["roofline_hbm"] = {
         "kernel": "k_gather (Schur complement: per-block gather of the observation records)", "bound": "hbm",
@@ -372,6 +379,27 @@ def ba_rooflines(out):
         "achieved": it_b / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "frac": it_b / (step_ms * 1e-3) / 1e9 / hbm_peak}
     out["lin_roofline"] = {"kernel": "k_lin", "bound": "hbm", "achieved": ba_lin_bytes(sc) / (kern_ms["k_lin"] * 1e-3) / 1e9,
                            "peak": hbm_peak, "unit": "GB/s"}
+
+
+def lba_latency(local_rank, n_windows=40):
+    """Per-solve latency of BASolver::LBA-sized problems (ba_solver.cc:523-591: a window of <= 8 frames, 5
+    iterations, 1e-4 / 1e-5) through xrb_ba_solve with host buffers — the call a mapper makes once per
+    registered frame (incremental_mapper.cc:71).  Single GPU."""
+    from xrsfm_b200 import ba, synth
+    sc = synth.make_sequential_scene(8, 3000, 6, 4242)
+    sc.pt_fixed[::3] = 1                        # SetUpLBA keeps well-triangulated points constant (:380-382)
+    solver = ba.BASolver(device=local_rank)
+    opts = dict(max_iterations=5, function_tolerance=1e-4, parameter_tolerance=1e-5)
+    for _ in range(3):
+        solver.solve_scene(sc.copy_state(), **opts)
+    t0 = time.perf_counter()
+    its = 0
+    for _ in range(n_windows):
+        its += solver.solve_scene(sc.copy_state(), **opts).num_lm_iterations
+    dt = time.perf_counter() - t0
+    return {"ms_per_solve": dt / n_windows * 1e3, "solves_per_s": n_windows / dt, "lm_iterations_per_solve": its / n_windows,
+            "window": {"frames": int(sc.n_cams), "points": int(sc.n_pts), "observations": int(sc.n_obs)},
+            "call": "xrb_ba_solve (load + <= 5 LM iterations + fetch, host buffers)"}
 
 
 def strip_private(out):
@@ -466,6 +494,28 @@ def run_match(args, rank, world, local_rank, n_feat=4096):
     m2.upload_packed(offs, hb)
     off, mm = m2.match_pairs(pairs)
     e2e_s = time.perf_counter() - t0
+    # per-pair compat path: what the UNCHANGED feature_processing.cc:118-154 drives through the façade —
+    # two host->device descriptor copies and one blocking read-back per pair
+    compat = None
+    if rank == 0:
+        import ctypes as C
+        n_cp = min(200, pairs.shape[0])
+        buf = np.zeros((n_feat, 2), dtype=np.uint32)
+        lib.xrb_match_set_descriptors.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        def one_pair(a, b):
+            lib.xrb_match_set_descriptors(m2._h, 0, n_feat, hb[a * n_feat:].ctypes.data, -1)
+            lib.xrb_match_set_descriptors(m2._h, 1, n_feat, hb[b * n_feat:].ctypes.data, -1)
+            return lib.xrb_match_get(m2._h, n_feat, buf.ctypes.data, 0.7, 0.8, 1)
+        for a, b in pairs[:5]:
+            one_pair(int(a), int(b))
+        t0 = time.perf_counter()
+        tot = 0
+        for a, b in pairs[:n_cp]:
+            tot += one_pair(int(a), int(b))
+        dt = time.perf_counter() - t0
+        compat = {"value": n_cp / dt, "unit": "pairs/s", "pairs": int(n_cp), "mean_matches": tot / n_cp,
+                  "call": "xrb_match_set_descriptors x2 + xrb_match_get per pair (pinned host buffers, blocking) — the "
+                          "like-for-like of reference_cuda_kernels below"}
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
@@ -498,6 +548,7 @@ def run_match(args, rank, world, local_rank, n_feat=4096):
                      "int8_tops": 2 * 128 * n_feat * n_feat / per_pair_s / 1e12,
                      "note": "binding roof is the integer-MAC pipe (tcgen05 kind::i8), not HBM: see DESIGN.md §M.4"},
         "mean_matches_per_pair": float(np.diff(off).mean()) if len(off) > 1 else 0.0,
+        "per_pair_compat": compat,
     }
 
 
@@ -605,6 +656,8 @@ def main():
             ba_rooflines(out)
             if not args.no_cpu_baseline:
                 out.update(parity_check(out["_scene"], out["_cfg"], 3, out["_conv_log"]))
+            if world == 1:
+                out["lba_latency"] = lba_latency(local_rank)
             if c4 is not None:
                 ba_rooflines(c4)
                 keep = ("value", "unit", "ms_per_step", "steps", "n_gpus", "config", "e2e", "kernel_ms_per_solve",

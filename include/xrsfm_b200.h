@@ -284,6 +284,33 @@ int xrb_ba_profile(const xrb_ba_solver *s, double ms[6], int64_t launches[6]);
 int xrb_debug_chol_trace(int enable, int64_t *out, int cap_records);
 int xrb_debug_tile_solve(int n, int bw, const double *A, const double *rhs, double *x_out, int reps,
                          double *ms_out);
+/* ---- Geometric verification of matched pairs (the step that follows path M) --------------------
+ * Replaces the loop body of FeatureMatching that calls SolveFundamnetalCOLMAP
+ * (src/feature/feature_processing.cc:256-296, src/geometry/epipolar_geometry.hpp:10-27):
+ * colmap::LORANSAC<7-point, 8-point> with the options below (defaults = the reference's), the squared
+ * Sampson error as residual, inlier count / residual sum as support.  One launch verifies a whole
+ * batch of pairs, one CTA per pair.  Each pair starts from a freshly seeded generator (std::mt19937,
+ * seed 0, restated bit for bit together with libstdc++'s uniform_int_distribution): the sample
+ * sequence is the one the reference draws for the first pair an OpenMP thread processes. */
+typedef struct xrb_fm_options {  /* colmap::RANSACOptions as epipolar_geometry.hpp:13-18 sets them */
+    double max_error, min_inlier_ratio, confidence;
+    int64_t min_num_trials, max_num_trials;
+} xrb_fm_options;
+typedef struct xrb_fm_report {
+    int32_t success, best_is_local;  /* best_is_local: the model came from the local optimisation */
+    int64_t num_trials, num_inliers;
+    double residual_sum;
+    double F[9];                     /* row-major, x2^T F x1 = 0 */
+} xrb_fm_report;
+void xrb_fm_default_options(xrb_fm_options *o);
+/* offsets[n_pairs+1]: matches of pair p are rows offsets[p] .. offsets[p+1] of pts1 / pts2 (x, y pairs of
+ * frame1.points[match.id1] / frame2.points[match.id2]); inlier_mask has offsets[n_pairs] entries.
+ * HOST pointers; a pair with fewer than 7 matches reports success = 0. */
+int xrb_fm_loransac_batch(int device, int n_pairs, const int64_t *offsets, const double *pts1, const double *pts2,
+                          const xrb_fm_options *opt, xrb_fm_report *reports, char *inlier_mask);
+/* host-only debug hook: the first `trials` samples (7 indices each) a fresh generator draws for n matches */
+int xrb_debug_fm_samples(int n, int trials, int32_t *out);
+
 /* Host-only debug hooks (no device needed): the symbolic plan (tile slots, task lists with the flag
  * values they wait for) of a tile pattern pat[nt x nt] (lower part), and the column order of a band.
  * counts[16] = nt, n_tiles, n_tiles_orig, n_f, n_w, n_b, n_wb, n_far, n_chain_f, n_chain_b, depth_f,

@@ -124,6 +124,12 @@ static int run_match(const char *desc, const char *out) {
             wr(o, ij, 2);
         }
     }
+    // (c) the fully GPU variant: matching + batched LO-RANSAC verification (the mock's points carry no real two-view
+    // geometry; the parity of the verification itself is tests/test_fm_gpu.py)
+    std::vector<mock::FramePair> verified;
+    const int rc2 = xrsfm_b200::FeatureMatching(frames, pairs, verified, true);
+    const int32_t tail[2] = {rc2, (int32_t)verified.size()};
+    wr(o, tail, 2);
     fclose(o);
     return 0;
 }

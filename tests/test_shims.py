@@ -181,3 +181,5 @@ def test_cpp_matcher_facade_and_feature_matching_on_gpu(tmp_path):
         got = raw[pos: pos + 2 * n].reshape(n, 2); pos += 2 * n
         assert (id1, id2, n, inl) == (a, b, exp.shape[0], exp.shape[0])
         assert (got == exp).all()
+    rc2, n_verified = (int(v) for v in raw[pos: pos + 2])  # (c) matching + batched GPU LO-RANSAC ran end to end
+    assert rc2 == 0 and 0 <= n_verified <= len(kept)

@@ -105,6 +105,10 @@ SIGNATURES = {
     "xrb_ba_profile_detail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "xrb_debug_chol_trace": (C.c_int, [C.c_int, C.c_void_p, C.c_int]),
     "xrb_debug_tile_solve": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "xrb_fm_default_options": (None, [C.c_void_p]),
+    "xrb_fm_loransac_batch": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
+    "xrb_debug_fm_samples": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
     "xrb_debug_chol_plan": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                       C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "xrb_debug_column_order": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -112,4 +112,76 @@ int FeatureMatching(const std::vector<FrameT> &frames, const std::vector<std::pa
     return XRB_OK;
 }
 
+// SolveFundamnetalCOLMAP for EVERY pair of the batch in one launch (xrb_fm_loransac_batch, one CTA per pair): the
+// verification callable of the overload above is replaced by a gather of the matched points, one call, and a
+// scatter of inlier_num / inlier_mask / F (row-major into frame_pair.F(r, c) when the pair type has it).
+namespace detail {
+template <class FP>
+auto set_F(FP &fp, const double *F, int) -> decltype(fp.F(0, 0), void()) {
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) fp.F(r, c) = F[r * 3 + c];
+}
+template <class FP>
+void set_F(FP &, const double *, long) {}
+}  // namespace detail
+
+template <class FrameT, class FramePairT>
+int FeatureMatching(const std::vector<FrameT> &frames, const std::vector<std::pair<int, int>> &candidate_pairs,
+                    std::vector<FramePairT> &frame_pairs, bool b_use_fundamental, int device = 0, int max_match = 16384) {
+    // pass 1: matching only (the stand-in verification marks nothing, so every pair is returned untouched)
+    std::vector<FramePairT> all;
+    {
+        auto keep_all = [](const auto &p1, const auto &, FramePairT &fp) {
+            fp.inlier_num = (int)p1.size();
+            fp.inlier_mask.assign(p1.size(), 1);
+        };
+        // thresholds would drop pairs below 15 matches: those are dropped by the reference as well (:260-262)
+        const int rc = FeatureMatching(frames, candidate_pairs, all, true, keep_all, device, max_match);
+        if (rc != XRB_OK) return rc;
+    }
+    if (!b_use_fundamental) return XRB_ERR_INVALID;  // the reference CHECK(false)s on this branch (:273)
+    std::vector<int64_t> offsets(all.size() + 1, 0);
+    for (size_t i = 0; i < all.size(); ++i) offsets[i + 1] = offsets[i] + (int64_t)all[i].matches.size();
+    std::vector<double> pts1(2 * (size_t)offsets.back()), pts2(2 * (size_t)offsets.back());
+    for (size_t i = 0; i < all.size(); ++i) {
+        const auto &f1 = frames[all[i].id1];
+        const auto &f2 = frames[all[i].id2];
+        int64_t w = offsets[i];
+        for (const auto &m : all[i].matches) {
+            pts1[2 * w] = f1.points[m.id1](0), pts1[2 * w + 1] = f1.points[m.id1](1);
+            pts2[2 * w] = f2.points[m.id2](0), pts2[2 * w + 1] = f2.points[m.id2](1);
+            ++w;
+        }
+    }
+    xrb_fm_options opt;
+    xrb_fm_default_options(&opt);  // epipolar_geometry.hpp:13-18
+    std::vector<xrb_fm_report> reports(all.size());
+    std::vector<char> mask((size_t)std::max<int64_t>(1, offsets.back()));
+    const int rc = xrb_fm_loransac_batch(device, (int)all.size(), offsets.data(), pts1.data(), pts2.data(), &opt, reports.data(),
+                                         mask.data());
+    if (rc != XRB_OK) {
+        std::fprintf(stderr, "xrb_fm_loransac_batch failed (%d): %s\n", rc, xrb_last_error());
+        return rc;
+    }
+    int count_inlier_pairs = 0;
+    for (size_t i = 0; i < all.size(); ++i) {
+        auto &fp = all[i];
+        const int n = (int)fp.matches.size();
+        fp.inlier_num = (int)reports[i].num_inliers;
+        detail::set_F(fp, reports[i].F, 0);
+        const int inlier_threshold = std::max(15, (int)(0.25 * n));  // :283-285
+        if (!reports[i].success || fp.inlier_num < inlier_threshold) continue;
+        using MatchT = typename std::decay<decltype(fp.matches[0])>::type;
+        std::vector<MatchT> inliers;
+        for (int k = 0; k < n; ++k)
+            if (mask[offsets[i] + k]) inliers.push_back(fp.matches[k]);
+        fp.inlier_mask.assign(inliers.size(), true);
+        fp.matches.swap(inliers);
+        frame_pairs.emplace_back(fp);
+        count_inlier_pairs++;
+    }
+    std::printf("matched image pairs: %d/%zu\n", count_inlier_pairs, candidate_pairs.size());
+    return XRB_OK;
+}
+
 }  // namespace xrsfm_b200
