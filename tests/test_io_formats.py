@@ -187,6 +187,14 @@ def test_colmap_write_updated_roundtrip(tmp_path):
     io_formats.WriteColMapDataBinary(d_in, d_out, pr)
     for name in ("cameras.bin", "images.bin", "points3D.bin"):
         assert open(d_ref + name, "rb").read() == open(d_out + name, "rb").read(), name
+    # the natural "write back after BA": same directory in and out, and an output directory that does not exist yet
+    io_formats.WriteColMapDataBinary(d_in, d_in, pr)
+    d_new = str(tmp_path / "made" / "deeper") + "/"
+    io_formats.WriteColMapDataBinary(d_in, d_new, pr)
+    for name in ("cameras.bin", "images.bin", "points3D.bin"):
+        assert open(d_ref + name, "rb").read() == open(d_in + name, "rb").read(), name
+        assert open(d_ref + name, "rb").read() == open(d_new + name, "rb").read(), name
+    assert sorted(os.listdir(d_in)) == ["cameras.bin", "images.bin", "points3D.bin"]  # no temporaries left
 
 
 def test_colmap_rejects_inconsistent_models(tmp_path):

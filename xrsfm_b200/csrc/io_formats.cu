@@ -6,6 +6,8 @@
 // Every reader is two-pass (scan sizes, then fill caller-owned flat arrays): the layouts the two
 // hot paths consume (packed descriptor block + row offsets, xrb_ba_problem) come straight off the
 // file, without the reference's per-frame / per-track objects in between.
+#include <sys/stat.h>
+
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -39,9 +41,10 @@ bool BinFile::open_write(const char *path) {
     pos_ = size_ = 0;
     return true;
 }
-void BinFile::close() {
-    if (f_) fclose(f_);
+bool BinFile::close() {
+    const bool ok = !f_ || fclose(f_) == 0;
     f_ = nullptr;
+    return ok;
 }
 bool BinFile::read(void *dst, size_t bytes) {
     if (!f_ || pos_ + (int64_t)bytes > size_) return false;
@@ -144,6 +147,16 @@ int fp_walk(const char *path, Fn &&fn) {
 namespace {
 
 std::string join(const char *dir, const char *file) { return std::string(dir ? dir : "") + file; }
+
+// mkdir -p of the directory part of `dir` (the path prefix callers pass ends with '/')
+void make_dirs(const char *dir) {
+    std::string d(dir ? dir : "");
+    for (size_t i = 1; i <= d.size(); ++i)
+        if (i == d.size() || d[i] == '/') {
+            const std::string sub = d.substr(0, i);
+            if (!sub.empty() && sub != "/" && sub.back() != '/') mkdir(sub.c_str(), 0777);
+        }
+}
 
 // points3D.bin: fn(index, id, xyz) per track, in file order
 template <class Fn>
@@ -292,7 +305,7 @@ int xrb_ftr_write(const char *path, int32_t n_frames, const int64_t *row_offsets
         }
         ok = ok && f.write(desc_block + 128 * r0, (size_t)np * 128);
     }
-    f.close();
+    ok = f.close() && ok;
     if (!ok) {
         set_error("ftr_write: write to %s failed", path);
         return XRB_ERR_INVALID;
@@ -412,7 +425,7 @@ int xrb_fp_write(const char *path, int64_t n_pairs, const int32_t (*ids)[2], con
             ok = ok && f.write(ones.data(), ones.size());
         }
     }
-    f.close();
+    ok = f.close() && ok;
     if (!ok) {
         set_error("fp_write: write to %s failed", path);
         return XRB_ERR_INVALID;
@@ -562,19 +575,30 @@ int xrb_colmap_write_updated(const char *dir_in, const char *dir_out, const xrb_
         return XRB_ERR_INVALID;
     }
     std::vector<unsigned char> buf;
+    // WriteColMapDataBinary creates the directory (io_ecim.cc); every file is written next to its target and
+    // renamed into place once complete, so dir_out == dir_in (write back after BA) is safe
+    make_dirs(dir_out);
+    auto publish = [](BinFile &in, BinFile &out, const std::string &tmp, const std::string &dst, bool ok) {
+        in.close();
+        ok = out.close() && ok;
+        if (ok && rename(tmp.c_str(), dst.c_str()) != 0) ok = false;
+        if (!ok) remove(tmp.c_str());
+        return ok;
+    };
     {   // cameras.bin: intrinsics are constant in the reference's BA (ba_solver.cc:608) — plain copy
         BinFile in, out;
-        const std::string pi = join(dir_in, "cameras.bin"), po = join(dir_out, "cameras.bin");
+        const std::string pi = join(dir_in, "cameras.bin"), po = join(dir_out, "cameras.bin"), pt = po + ".xrb_tmp";
         if (!in.open_read(pi.c_str())) return cannot_open(pi.c_str());
-        if (!out.open_write(po.c_str())) return cannot_open(po.c_str());
+        if (!out.open_write(pt.c_str())) return cannot_open(pt.c_str());
         buf.resize((size_t)in.size());
-        if (!in.read(buf.data(), buf.size()) || !out.write(buf.data(), buf.size())) return bad_file(in, "cameras.bin: copy failed");
+        const bool ok = in.read(buf.data(), buf.size()) && out.write(buf.data(), buf.size());
+        if (!publish(in, out, pt, po, ok)) return bad_file(out, "cameras.bin: copy failed");
     }
     {   // images.bin: q (w x y z) and t replaced frame by frame
         BinFile in, out;
-        const std::string pi = join(dir_in, "images.bin"), po = join(dir_out, "images.bin");
+        const std::string pi = join(dir_in, "images.bin"), po = join(dir_out, "images.bin"), pt = po + ".xrb_tmp";
         if (!in.open_read(pi.c_str())) return cannot_open(pi.c_str());
-        if (!out.open_write(po.c_str())) return cannot_open(po.c_str());
+        if (!out.open_write(pt.c_str())) return cannot_open(pt.c_str());
         uint64_t n = 0;
         if (!in.get(&n) || (int64_t)n != sizes->n_frames) return bad_file(in, "images.bin: frame count differs from sizes");
         bool ok = out.put(n);
@@ -593,13 +617,13 @@ int xrb_colmap_write_updated(const char *dir_in, const char *dir_out, const xrb_
             ok = out.put(id) && out.write(qw, 32) && out.write(t, 24) && out.put(cam) &&
                  out.write(name.c_str(), name.size() + 1) && out.put(n_p2d) && out.write(buf.data(), buf.size());
         }
-        if (!ok) return bad_file(out, "images.bin: write failed");
+        if (!publish(in, out, pt, po, ok)) return bad_file(out, "images.bin: write failed");
     }
     {   // points3D.bin: xyz replaced track by track
         BinFile in, out;
-        const std::string pi = join(dir_in, "points3D.bin"), po = join(dir_out, "points3D.bin");
+        const std::string pi = join(dir_in, "points3D.bin"), po = join(dir_out, "points3D.bin"), pt = po + ".xrb_tmp";
         if (!in.open_read(pi.c_str())) return cannot_open(pi.c_str());
-        if (!out.open_write(po.c_str())) return cannot_open(po.c_str());
+        if (!out.open_write(pt.c_str())) return cannot_open(pt.c_str());
         uint64_t n = 0;
         if (!in.get(&n) || (int64_t)n != sizes->n_points) return bad_file(in, "points3D.bin: track count differs from sizes");
         bool ok = out.put(n);
@@ -615,7 +639,7 @@ int xrb_colmap_write_updated(const char *dir_in, const char *dir_out, const xrb_
             ok = out.put(id) && out.write(prob->pts + 3 * i, 24) && out.write(rgb, 3) && out.put(err) && out.put(n_obs) &&
                  out.write(buf.data(), buf.size());
         }
-        if (!ok) return bad_file(out, "points3D.bin: write failed");
+        if (!publish(in, out, pt, po, ok)) return bad_file(out, "points3D.bin: write failed");
     }
     return XRB_OK;
 }

@@ -18,7 +18,7 @@ class BinFile {
     ~BinFile() { close(); }
     bool open_read(const char *path);
     bool open_write(const char *path);
-    void close();
+    bool close();  // false when the final flush failed (ENOSPC, EIO): writers fold it into their status
     bool read(void *dst, size_t bytes);
     bool skip(int64_t bytes);
     bool write(const void *src, size_t bytes);
