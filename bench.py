@@ -397,9 +397,17 @@ def lba_latency(local_rank, n_windows=40):
     for _ in range(n_windows):
         its += solver.solve_scene(sc.copy_state(), **opts).num_lm_iterations
     dt = time.perf_counter() - t0
+    # the same windows through the batched entry point (8 engines on this device)
+    batch = [sc.copy_state() for _ in range(4 * n_windows)]
+    ba.BASolver.solve_batch(batch[:16], device=local_rank, n_workers=8, **opts)
+    t0 = time.perf_counter()
+    ba.BASolver.solve_batch(batch, device=local_rank, n_workers=8, **opts)
+    dtb = time.perf_counter() - t0
     return {"ms_per_solve": dt / n_windows * 1e3, "solves_per_s": n_windows / dt, "lm_iterations_per_solve": its / n_windows,
             "window": {"frames": int(sc.n_cams), "points": int(sc.n_pts), "observations": int(sc.n_obs)},
-            "call": "xrb_ba_solve (load + <= 5 LM iterations + fetch, host buffers)"}
+            "call": "xrb_ba_solve (load + <= 5 LM iterations + fetch, host buffers)",
+            "batched": {"solves_per_s": len(batch) / dtb, "windows": len(batch), "engines": 8,
+                        "call": "xrb_ba_solve_batch (same windows, 8 engines on one device)"}}
 
 
 def strip_private(out):

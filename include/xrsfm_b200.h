@@ -253,6 +253,15 @@ int xrb_ba_fetch(xrb_ba_solver *s, xrb_ba_problem *prob);
  * ReProjectionCost::operator() (cost_factor_ceres.h:19-40) over the whole problem. */
 int xrb_ba_residuals(xrb_ba_solver *s, double *out_residuals);
 
+/* Batched local bundle adjustment: n_problems independent problems (the <= 8-frame windows BASolver::LBA
+ * builds, ba_solver.cc:523-591, called once per registered frame at src/mapper/incremental_mapper.cc:71; or
+ * pose refinements) solved concurrently on one device by n_workers engines (<= 0: 8), each with its own
+ * streams, so that the per-solve launch and synchronisation latencies overlap.  Every problem gets exactly
+ * what xrb_ba_solve would give it (same options for all; states updated in place, one summary each).
+ * Returns the first failure, after all problems were attempted. */
+int xrb_ba_solve_batch(int device, int n_problems, const xrb_ba_problem *problems, const xrb_ba_options *opt,
+                       xrb_ba_summary *summaries, int n_workers);
+
 /* Post-BA point filter on the solver's CURRENT state (after xrb_ba_run / xrb_ba_solve; single GPU).
  * Replaces Point3dProcessor::FilterPoints3d(map, max_re, deg) (src/geometry/track_processor.cc:321-349,
  * FilterPoint3d :279-319, UpdateTrackAngle :253-277, Reprojection_Error :19-26), which the mapper calls

@@ -99,6 +99,7 @@ SIGNATURES = {
     "xrb_ba_run": (C.c_int, [C.c_void_p, C.POINTER(BAOptions), C.POINTER(BASummary), C.c_void_p]),
     "xrb_ba_fetch": (C.c_int, [C.c_void_p, C.POINTER(BAProblem)]),
     "xrb_ba_residuals": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "xrb_ba_solve_batch": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(BAOptions), C.c_void_p, C.c_int]),
     "xrb_ba_filter_points3d": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "xrb_ba_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

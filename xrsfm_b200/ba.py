@@ -152,6 +152,16 @@ class BASolver:
         names = ("schur", "solve", "backsub", "cost", "exchange", "run")
         return {n: (ms[i], ln[i]) for i, n in enumerate(names)}
 
+    @staticmethod
+    def solve_batch(scenes, device=0, n_workers=8, **opts):
+        """xrb_ba_solve_batch: independent (local-BA sized) problems solved concurrently on one device."""
+        probs = (_lib.BAProblem * len(scenes))(*[make_problem(sc) for sc in scenes])
+        sums = (_lib.BASummary * len(scenes))()
+        o = make_options(**opts)
+        _lib.check(_lib.lib().xrb_ba_solve_batch(device, len(scenes), probs, C.byref(o), sums, n_workers),
+                   "xrb_ba_solve_batch")
+        return list(sums)
+
     def filter_points3d(self, max_re, deg):
         """Point3dProcessor::FilterPoints3d (track_processor.cc:321-349) on the solver's current state.
         Returns (keep_obs, pt_outlier, pt_error, pt_angle, (num_filtered1, num_filtered2))."""

@@ -12,7 +12,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <map>
+#include <mutex>
 #include <numeric>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "ba_structure.cuh"
@@ -54,6 +59,7 @@ struct xrb_ba_solver {
     int nc = 0, bw = 0;       // nc: padded dimension of the reduced camera system (a multiple of 64)
     int nc_true = 0, parts = 1;  // variable camera columns; independent interiors of the column order
     CholPlan plan;
+    CholWorkspace chol_ws;
     DevBuf d_holes, d_pat;
     int n_holes = 0;
     int n_var_q = 0, n_var_t = 0, n_var_pts = 0, n_res_blocks = 0;
@@ -340,7 +346,7 @@ int compute_step(xrb_ba_solver *s, const BAConsts &k, double radius, cudaStream_
     ev[2].rec(st);
     if ((rc = ba_launch_set_holes(L, s->d_holes.as<int32_t>(), s->n_holes, st))) return rc;
     if ((rc = ba_launch_cam_diag(P, x, L, inv_radius, s->scalL(), st))) return rc;
-    if ((rc = ba_launch_tile_cholesky_solve(s->plan.d, L.S, L.rhs, s->d_linv.as<double>(), s->d_yc.as<double>(),
+    if ((rc = ba_launch_tile_cholesky_solve(s->plan.d, s->chol_ws, L.S, L.rhs, s->d_linv.as<double>(), s->d_yc.as<double>(),
                                             s->scalL() + SC_FAIL, st, &s->launches[1])))
         return rc;
     s->launches[1]++;
@@ -677,6 +683,7 @@ void xrb_ba_destroy(xrb_ba_solver *s) {
                       &s->d_Tt, &s->d_h, &s->d_holes, &s->d_pat};
     for (DevBuf *b : bufs) b->release();
     s->plan.release();
+    s->chol_ws.release();
     s->W.release();
     for (int i = 0; i < 3; ++i) s->d_q[i].release(), s->d_t[i].release(), s->d_X[i].release();
     if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -798,6 +805,53 @@ int xrb_ba_residuals(xrb_ba_solver *s, double *out) {
     return rc;
 }
 
+/* Many small problems (local-BA windows) on one device: see include/xrsfm_b200.h */
+int xrb_ba_solve_batch(int device, int n_problems, const xrb_ba_problem *problems, const xrb_ba_options *opt,
+                       xrb_ba_summary *summaries, int n_workers) {
+    if (n_problems < 0 || !opt || (n_problems && (!problems || !summaries))) {
+        set_error("ba_solve_batch: bad arguments");
+        return XRB_ERR_INVALID;
+    }
+    if (n_problems == 0) return XRB_OK;
+    n_workers = std::max(1, std::min(std::min(n_workers <= 0 ? 8 : n_workers, 32), n_problems));
+    // one engine per worker and device, kept for the life of the process (their buffers are grow-only)
+    static std::mutex pool_mutex;
+    static std::map<int, std::vector<xrb_ba_solver *>> pool;
+    std::vector<xrb_ba_solver *> engines;
+    {
+        std::lock_guard<std::mutex> lock(pool_mutex);
+        std::vector<xrb_ba_solver *> &mine = pool[device];
+        while ((int)mine.size() < n_workers) {
+            xrb_ba_solver *h = xrb_ba_create(device);
+            if (!h) return XRB_ERR_NO_DEVICE;
+            mine.push_back(h);
+        }
+        engines.assign(mine.begin(), mine.begin() + n_workers);
+    }
+    static std::mutex run_mutex;  // one batch at a time per process: the engines are not shared between batches
+    std::lock_guard<std::mutex> run_lock(run_mutex);
+    std::atomic<int> next{0}, first_rc{XRB_OK};
+    std::string first_error;
+    std::mutex err_mutex;
+    auto work = [&](xrb_ba_solver *h) {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n_problems) break;
+            const int rc = xrb_ba_solve(h, &problems[i], opt, &summaries[i]);
+            if (rc != XRB_OK) {
+                std::lock_guard<std::mutex> lock(err_mutex);
+                if (first_rc.load() == XRB_OK) first_rc = rc, first_error = xrb_last_error();
+            }
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int w = 1; w < n_workers; ++w) threads.emplace_back(work, engines[w]);
+    work(engines[0]);
+    for (auto &t : threads) t.join();
+    if (first_rc.load() != XRB_OK) set_error("ba_solve_batch: %s", first_error.c_str());
+    return first_rc.load();
+}
+
 /* Post-BA filter on the solver's current state (single GPU): see include/xrsfm_b200.h */
 int xrb_ba_filter_points3d(xrb_ba_solver *s, double max_re, double deg, uint8_t *keep_obs, uint8_t *pt_outlier,
                            double *pt_error, double *pt_angle, int32_t counts[2]) {
@@ -869,6 +923,7 @@ int xrb_debug_tile_solve(int n, int bw, const double *A, const double *rhs, doub
     for (int r = n; r < np; ++r) packed[at(r, r)] = 1.0;
     for (int r = 0; r < n; ++r) packed[nS + r] = rhs[r];
     DevBuf E, dinv, x, fail;
+    CholWorkspace ws;
     if ((rc = E.reserve(packed.size() * 8)) || (rc = dinv.reserve((size_t)(nt + 1) * 1024 * 8)) ||
         (rc = x.reserve(nR * 8)) || (rc = fail.reserve(8)))
         return rc;
@@ -880,7 +935,7 @@ int xrb_debug_tile_solve(int n, int bw, const double *A, const double *rhs, doub
         cudaMemsetAsync(fail.p, 0, 8, st);
         cudaMemsetAsync(x.p, 0, nR * 8, st);
         cudaEventRecord(e0, st);
-        rc = ba_launch_tile_cholesky_solve(plan.d, E.as<double>(), E.as<double>() + nS, dinv.as<double>(), x.as<double>(),
+        rc = ba_launch_tile_cholesky_solve(plan.d, ws, E.as<double>(), E.as<double>() + nS, dinv.as<double>(), x.as<double>(),
                                            fail.as<double>(), st, nullptr);
         cudaEventRecord(e1, st);
         if (cudaStreamSynchronize(st) != cudaSuccess) rc = XRB_ERR_CUDA;
@@ -902,7 +957,7 @@ int xrb_debug_tile_solve(int n, int bw, const double *A, const double *rhs, doub
     if (ms_out) *ms_out = best;
     cudaEventDestroy(e0), cudaEventDestroy(e1);
     cudaStreamDestroy(st);
-    E.release(), dinv.release(), x.release(), fail.release(), plan.release();
+    E.release(), dinv.release(), x.release(), fail.release(), plan.release(), ws.release();
     return rc;
 }
 

@@ -116,11 +116,15 @@ int ba_launch_filter(const BAProblemDev &P, const BAStateDev &st, const int32_t 
 // ba_tilechol.cu — sparse tile Cholesky of S in one persistent kernel (task DAG over resident CTAs,
 // flags in global memory), forward substitution folded in (rhs -> y), back-substitution in a second
 // kernel.  dinv: nt x 4 x 256 doubles (inverses of the 16 x 16 diagonal blocks of L).
-int ba_launch_tile_cholesky_solve(const CholPlanDev &plan, double *tiles, double *rhs, double *dinv, double *x_out,
-                                  double *fail_flag, cudaStream_t st, int64_t *launches);
+struct CholWorkspace {  // per solver: dependency flags and partial sums of one factorisation in flight
+    DevBuf flags, wpart;
+    void release();
+};
+int ba_launch_tile_cholesky_solve(const CholPlanDev &plan, CholWorkspace &ws, double *tiles, double *rhs, double *dinv,
+                                  double *x_out, double *fail_flag, cudaStream_t st, int64_t *launches);
 // identity rows of the padding columns (tile-aligned parts, matrix end): S[c][c] = 1 for the listed columns
 int ba_launch_set_holes(const BALinSys &L, const int32_t *holes, int n_holes, cudaStream_t st);
-int ba_tile_cholesky_aborted(int *aborted);
+int ba_tile_cholesky_aborted(const CholWorkspace &ws, int *aborted);
 // debug: clock64 of the chain CTA after each block column of the last factorisation
 int ba_tile_cholesky_trace(int enable, long long *out, int cap);
 

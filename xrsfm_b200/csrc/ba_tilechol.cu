@@ -764,24 +764,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_tile_backsolve(CholArgs A) {
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-struct TileCtx {
-    int *flags = nullptr;
-    size_t flags_cap = 0;
-    double *wpart = nullptr;
-    size_t wpart_cap = 0;
-    long long *trace = nullptr;
+struct DeviceInfo {
     int grid = 0;
     bool attr_set = false;
+    long long *trace = nullptr;
 };
 constexpr int kMaxDevices = 64;
-TileCtx g_tctx[kMaxDevices];
+DeviceInfo g_dev[kMaxDevices];
 std::mutex g_tmutex;
 bool g_trace_on = false;
 
 }  // namespace
 
-int ba_launch_tile_cholesky_solve(const CholPlanDev &plan, double *tiles, double *rhs, double *dinv, double *x_out,
-                                  double *fail_flag, cudaStream_t st, int64_t *launches) {
+void CholWorkspace::release() { flags.release(), wpart.release(); }
+
+// `ws` belongs to the calling solver: several solvers may factor on one device at the same time
+// (batched local BA), each with its own flags and partial sums.
+int ba_launch_tile_cholesky_solve(const CholPlanDev &plan, CholWorkspace &ws, double *tiles, double *rhs, double *dinv,
+                                  double *x_out, double *fail_flag, cudaStream_t st, int64_t *launches) {
     if (plan.nt <= 0) return XRB_OK;
     int dev = 0;
     XRB_CUDA(cudaGetDevice(&dev));
@@ -789,46 +789,42 @@ int ba_launch_tile_cholesky_solve(const CholPlanDev &plan, double *tiles, double
         set_error("cholesky: device id %d outside [0, %d)", dev, kMaxDevices);
         return XRB_ERR_INVALID;
     }
-    std::lock_guard<std::mutex> lock(g_tmutex);
-    TileCtx &ctx = g_tctx[dev];
-    if (!ctx.attr_set) {
-        XRB_CUDA(cudaFuncSetAttribute(k_tile_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        XRB_CUDA(cudaFuncSetAttribute(k_tile_backsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        int sms = 0, per_sm = 0, coop = 0;
-        XRB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        XRB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-        XRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_cholesky, kThreads, kSmemBytes));
-        if (!coop || per_sm < 1) {
-            set_error("cholesky: the device cannot co-schedule the persistent factorisation kernel");
-            return XRB_ERR_NO_DEVICE;
+    int grid = 0;
+    long long *trace = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_tmutex);
+        DeviceInfo &di = g_dev[dev];
+        if (!di.attr_set) {
+            XRB_CUDA(cudaFuncSetAttribute(k_tile_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+            XRB_CUDA(cudaFuncSetAttribute(k_tile_backsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+            int sms = 0, per_sm = 0, coop = 0;
+            XRB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            XRB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+            XRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_cholesky, kThreads, kSmemBytes));
+            if (!coop || per_sm < 1) {
+                set_error("cholesky: the device cannot co-schedule the persistent factorisation kernel");
+                return XRB_ERR_NO_DEVICE;
+            }
+            di.grid = sms;  // one CTA per SM
+            di.attr_set = true;
         }
-        ctx.grid = sms;  // one CTA per SM
-        ctx.attr_set = true;
+        if (g_trace_on && !di.trace) XRB_CUDA(cudaMalloc(&di.trace, (4096 + 16) * sizeof(long long)));
+        grid = di.grid;
+        trace = g_trace_on ? di.trace : nullptr;
     }
     const size_t nflags = Flags::count(plan.nt, plan.n_tiles);
-    if (ctx.flags_cap < nflags) {
-        if (ctx.flags) cudaFree(ctx.flags);
-        ctx.flags = nullptr, ctx.flags_cap = 0;
-        XRB_CUDA(cudaMalloc(&ctx.flags, nflags * sizeof(int)));
-        ctx.flags_cap = nflags;
-    }
-    const size_t nw = 2 * (size_t)plan.nt * T;
-    if (ctx.wpart_cap < nw) {
-        if (ctx.wpart) cudaFree(ctx.wpart);
-        ctx.wpart = nullptr, ctx.wpart_cap = 0;
-        XRB_CUDA(cudaMalloc(&ctx.wpart, nw * sizeof(double)));
-        ctx.wpart_cap = nw;
-    }
-    if (g_trace_on && !ctx.trace) XRB_CUDA(cudaMalloc(&ctx.trace, (4096 + 16) * sizeof(long long)));
-    if (g_trace_on) XRB_CUDA(cudaMemsetAsync(ctx.trace, 0, (4096 + 16) * sizeof(long long), st));
-    XRB_CUDA(cudaMemsetAsync(ctx.flags, 0, nflags * sizeof(int), st));
+    int rc;
+    if ((rc = ws.flags.reserve(nflags * sizeof(int)))) return rc;
+    if ((rc = ws.wpart.reserve(2 * (size_t)plan.nt * T * sizeof(double)))) return rc;
+    if (trace) XRB_CUDA(cudaMemsetAsync(trace, 0, (4096 + 16) * sizeof(long long), st));
+    XRB_CUDA(cudaMemsetAsync(ws.flags.p, 0, nflags * sizeof(int), st));
     CholArgs A;
-    A.p = plan, A.tiles = tiles, A.rhs = rhs, A.dinv = dinv, A.x = x_out, A.wpart = ctx.wpart, A.fail = fail_flag;
-    A.f = Flags{ctx.flags, plan.nt, plan.n_tiles};
-    A.trace = g_trace_on ? ctx.trace : nullptr;
+    A.p = plan, A.tiles = tiles, A.rhs = rhs, A.dinv = dinv, A.x = x_out, A.wpart = ws.wpart.as<double>(), A.fail = fail_flag;
+    A.f = Flags{ws.flags.as<int>(), plan.nt, plan.n_tiles};
+    A.trace = trace;
     // CTAs beyond the number of tasks would only poll a counter once
-    const int grid_f = std::max(1, std::min(ctx.grid, plan.n_chain_f + plan.n_w));
-    const int grid_b = std::max(1, std::min(ctx.grid, plan.n_chain_b + plan.n_wb));
+    const int grid_f = std::max(1, std::min(grid, plan.n_chain_f + plan.n_w));
+    const int grid_b = std::max(1, std::min(grid, plan.n_chain_b + plan.n_wb));
     void *args[] = {&A};
     XRB_CUDA(cudaLaunchCooperativeKernel((void *)k_tile_cholesky, dim3(grid_f), dim3(kThreads), args, kSmemBytes, st));
     XRB_CUDA(cudaLaunchCooperativeKernel((void *)k_tile_backsolve, dim3(grid_b), dim3(kThreads), args, kSmemBytes, st));
@@ -838,13 +834,9 @@ int ba_launch_tile_cholesky_solve(const CholPlanDev &plan, double *tiles, double
 }
 
 // after a solve has completed (stream synchronised): did a wait give up?
-int ba_tile_cholesky_aborted(int *aborted) {
-    int dev = 0;
-    XRB_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_tmutex);
-    TileCtx &ctx = g_tctx[dev];
+int ba_tile_cholesky_aborted(const CholWorkspace &ws, int *aborted) {
     *aborted = 0;
-    if (ctx.flags) XRB_CUDA(cudaMemcpy(aborted, ctx.flags + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    if (ws.flags.p) XRB_CUDA(cudaMemcpy(aborted, ws.flags.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost));
     return XRB_OK;
 }
 
@@ -858,11 +850,11 @@ int ba_tile_cholesky_trace(int enable, long long *out, int cap) {
         return 0;
     }
     g_trace_on = false;
-    TileCtx &ctx = g_tctx[dev];
-    if (!ctx.trace || !out) return 0;
+    DeviceInfo &di = g_dev[dev];
+    if (!di.trace || !out) return 0;
     XRB_CUDA(cudaDeviceSynchronize());
     const int n = std::min(cap, 4096 + 16);
-    XRB_CUDA(cudaMemcpy(out, ctx.trace, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
+    XRB_CUDA(cudaMemcpy(out, di.trace, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
     return n;
 }
 
