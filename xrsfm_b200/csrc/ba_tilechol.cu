@@ -264,46 +264,54 @@ __device__ __forceinline__ double row_dot(const double *Xs, const double *y) {
     return s;
 }
 
-// ---- 16 x 16 factor of one warp, entirely in registers (row per lane, values exchanged by
-// shuffles, pivots through rsqrt).  Spelled as template recursion so that everything stays in
-// registers (with `#pragma unroll` the triangular loops stayed rolled and a[] went to local memory).
+// ---- Cholesky of the 64 x 64 diagonal tile in shared memory --------------------------------------
+// Per 16 columns (a "panel") the only serial work is the panel itself, and it lives in ONE warp's
+// registers: lane l holds rows b + l and b + 32 + l of the panel, column values travel by shuffles.
+// Within the panel the column-to-column dependency is the next pivot alone:
+//     d' = a[J+1][J+1] - a[J+1][J]^2 / d      (reciprocal by MUFU seed + two Newton steps)
+// which lane J+1 forms and broadcasts first; the scaling by rsqrt(d) and the rank-1 update of the other
+// columns follow in its shadow.  Everything else runs on the other warps while warp 0 is in the next
+// panel: the update of the far columns (DMMA on 8 x 8 fragments), the 16 x 16 block inverse, and the
+// right-hand side, which rides along as row 64 (forward substitution + its own updates, one panel behind).
+__device__ __forceinline__ double rcp_nr(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+}
 template <int J, int C>
-__device__ __forceinline__ void fac_upd(double (&a)[SB]) {
+__device__ __forceinline__ void fac2_upd(double (&a1)[SB], double (&a2)[SB]) {
     if constexpr (C < SB) {
-        const double lcj = __shfl_sync(0xFFFFFFFFu, a[J], C);  // L[C][J]
-        a[C] = fma(-a[J], lcj, a[C]);
-        fac_upd<J, C + 1>(a);
+        const double lcj = __shfl_sync(0xFFFFFFFFu, a1[J], C);  // L[b + C][b + J]: the diagonal block's rows sit in lanes 0..15
+        a1[C] = fma(-a1[J], lcj, a1[C]);
+        a2[C] = fma(-a2[J], lcj, a2[C]);
+        fac2_upd<J, C + 1>(a1, a2);
     }
 }
 template <int J>
-__device__ __forceinline__ void fac_col(double (&a)[SB], const int rl, double &inv_mine, bool &bad) {
+__device__ __forceinline__ void fac2_col(double (&a1)[SB], double (&a2)[SB], const int lane, double d, double &inv_mine,
+                                         bool &bad) {
     if constexpr (J < SB) {
-        double d = __shfl_sync(0xFFFFFFFFu, a[J], J);
         if (!(d > 0.0) || !isfinite(d)) bad = true, d = 1.0;
+        double dnext = 1.0;
+        if constexpr (J + 1 < SB) {
+            const double rd = rcp_nr(d);
+            const double dn = fma(-(a1[J] * a1[J]), rd, a1[J + 1]);  // meaningful on lane J + 1
+            dnext = __shfl_sync(0xFFFFFFFFu, dn, J + 1);
+        }
         const double inv = rsqrt(d);
-        if (rl == J) inv_mine = inv;
-        a[J] *= inv;
-        fac_upd<J, J + 1>(a);
-        fac_col<J + 1>(a, rl, inv_mine, bad);
+        if (lane == J) inv_mine = inv;
+        a1[J] *= inv, a2[J] *= inv;
+        fac2_upd<J, J + 1>(a1, a2);
+        if constexpr (J + 1 < SB) {
+            if (lane == J + 1) a1[J + 1] = dnext;  // one value for the pivot, the one its rsqrt sees
+        }
+        fac2_col<J + 1>(a1, a2, lane, dnext, inv_mine, bad);
     }
 }
-// rows below a factored 16-block: one thread per row, right-looking forward substitution
-template <int C, int C2>
-__device__ __forceinline__ void trsm_upd(double (&a)[SB], const double x, double (*A)[PA], const int b) {
-    if constexpr (C2 < SB) {
-        a[C2] = fma(-x, A[b + C2][b + C], a[C2]);
-        trsm_upd<C, C2 + 1>(a, x, A, b);
-    }
-}
-template <int C>
-__device__ __forceinline__ void trsm_col(double (&a)[SB], double (*A)[PA], const double *dinvd, const int b) {
-    if constexpr (C < SB) {
-        const double x = a[C] * dinvd[b + C];
-        a[C] = x;
-        trsm_upd<C, C + 1>(a, x, A, b);
-        trsm_col<C + 1>(a, A, dinvd, b);
-    }
-}
+
 // inverse of a factored 16-block out of shared memory: lane rl owns column rl of X = L^-1
 template <int R, int P>
 __device__ __forceinline__ void inv_dot(const double (&x)[SB], double (*A)[PA], const int b, double &v0, double &v1) {
@@ -325,83 +333,115 @@ __device__ __forceinline__ void inv_row(double (&x)[SB], double (*A)[PA], const 
         inv_row<R + 1>(x, A, dinvd, b, rl);
     }
 }
-
-// rank-16 update of rows [lo, 64] x columns [c0, c1) of D (lower part of the region
-// as far as it is lower in D) from panel columns [pb, pb + 16): D[i][j] -= sum_p D[i][pb+p] D[j][pb+p].
-// `nthr` threads with ids `t` share the outputs.
-__device__ __forceinline__ void rank16_update(double (*D)[PA], int pb, int r_lo, int c_lo, int c_hi, int t, int nthr) {
-    const int nr = T + 1 - r_lo, ncol = c_hi - c_lo;  // row 64 is the right-hand side riding along
-    for (int idx = t; idx < nr * ncol; idx += nthr) {
-        const int i = r_lo + idx / ncol, j = c_lo + idx % ncol;
-        if (j > i) continue;
-        double s0 = 0.0, s1 = 0.0;
+__device__ __forceinline__ void block_inverse(double (*D)[PA], const double *dinvd, double *Dinv, const int b) {
+    const int lane = threadIdx.x & 31, rl = lane & 15;
+    double x[SB];
+    inv_row<0>(x, D, dinvd, b, rl);
+    if (lane < SB) {
+        double *X = Dinv + (b / SB) * SB * PD;
 #pragma unroll
-        for (int p = 0; p < SB; p += 2) {
-            s0 = fma(D[i][pb + p], D[j][pb + p], s0);
-            s1 = fma(D[i][pb + p + 1], D[j][pb + p + 1], s1);
-        }
-        D[i][j] -= s0 + s1;
+        for (int r = 0; r < SB; ++r) X[r * PD + rl] = x[r];  // X[r][rl]; zero above the diagonal by construction
     }
+}
+
+// one 8 x 8 fragment of the trailing update from panel columns [pb, pb + 16):
+// D[8 fr + .][8 fc + .] -= D[8 fr + .][pb ..] D[8 fc + .][pb ..]^T  (one warp, four DMMAs)
+__device__ __forceinline__ void frag_update(double (*D)[PA], const int pb, const int fr, const int fc) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double acc[2] = {0.0, 0.0};
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) dmma(acc, D[8 * fr + g][pb + 4 * ks + t], D[8 * fc + g][pb + 4 * ks + t]);
+    D[8 * fr + g][8 * fc + 2 * t] -= acc[0];
+    D[8 * fr + g][8 * fc + 2 * t + 1] -= acc[1];
+}
+
+// row 64 (the right-hand side) against panel pb: forward substitution of its 16 entries (lane c owns
+// entry c, the solved ones are broadcast), then its share of the trailing update
+__device__ __forceinline__ void rhs_row_step(double (*D)[PA], const double *dinvd, const int pb, const bool last) {
+    const int lane = threadIdx.x & 31;
+    double r = lane < SB ? D[T][pb + lane] : 0.0, x = 0.0;
+#pragma unroll
+    for (int p = 0; p < SB; ++p) {
+        const double xp = __shfl_sync(0xFFFFFFFFu, r * dinvd[pb + p], p);
+        if (lane == p) x = xp;
+        if (lane > p && lane < SB) r = fma(-xp, D[pb + lane][pb + p], r);
+    }
+    if (lane < SB) D[T][pb + lane] = x;
+    __syncwarp();
+    if (!last)
+        for (int c2 = pb + SB + lane; c2 < T; c2 += 32) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int p = 0; p < SB; p += 2) {
+                s0 = fma(D[T][pb + p], D[c2][pb + p], s0);
+                s1 = fma(D[T][pb + p + 1], D[c2][pb + p + 1], s1);
+            }
+            D[T][c2] -= s0 + s1;
+        }
 }
 
 // In-place Cholesky of the 64 x 64 tile in shared memory D (lower part); dinvd[64] receives
 // 1 / L[r][r], Dinv[4][16][PD] the inverses of the four 16 x 16 diagonal blocks of L.
-// Row 64 of D holds the right-hand side of this block column: it is treated as one more row below
-// the tile, so that it leaves as y = L^-1 rhs (the forward substitution costs no extra step).
-// Serial chain per 16 columns: in-register factor (warp 0) -> rows below (one thread per row) ->
-// update of the NEXT 16 columns; the rest of the trailing update runs on warps 1..7 while warp 0
-// already factors the next block, the 16-block inverse on warp 7.
+// Row 64 of D holds the right-hand side of this block column and leaves as y = L^-1 rhs.
 __device__ __forceinline__ void potrf64(double (*D)[PA], double *dinvd, double *Dinv, bool &bad_out, long long *tr = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bool bad = false;
     for (int b = 0; b < T; b += SB) {
+        // ---- phase 1: warp 0 factors panel b; the others finish panel b - 16
         if (warp == 0) {
-            const int rl = lane & 15;
-            double a[SB];
+            const int r1 = b + lane, r2 = b + 32 + lane;
+            double a1[SB], a2[SB];
 #pragma unroll
-            for (int c = 0; c < SB; ++c) a[c] = D[b + rl][b + c];
+            for (int c = 0; c < SB; ++c) a1[c] = r1 < T ? D[r1][b + c] : 0.0, a2[c] = r2 < T ? D[r2][b + c] : 0.0;
             double inv_mine = 1.0;
-            fac_col<0>(a, rl, inv_mine, bad);
-            if (tr && b == 0 && tid == 0) tr[11] = clock64();
+            fac2_col<0>(a1, a2, lane, __shfl_sync(0xFFFFFFFFu, a1[0], 0), inv_mine, bad);
             if (lane < SB) {
 #pragma unroll
                 for (int c = 0; c < SB; ++c)
-                    if (c <= rl) D[b + rl][b + c] = a[c];
-                dinvd[b + rl] = inv_mine;
+                    if (c <= lane) D[r1][b + c] = a1[c];
+                dinvd[r1] = inv_mine;
+            } else if (r1 < T) {
+#pragma unroll
+                for (int c = 0; c < SB; ++c) D[r1][b + c] = a1[c];
             }
-        } else if (b >= SB && b + SB < T) {
-            // rest of the update of the previous step: rows [b+16, 64], columns [b+16, 64) from panel columns [b-16, b)
-            rank16_update(D, b - SB, b + SB, b + SB, T, tid - 32, kThreads - 32);
-        }
-        __syncthreads();
-        const int below = T - b - SB;
-        if (warp == 7) {
-            const int rl = lane & 15;
-            double x[SB];
-            inv_row<0>(x, D, dinvd, b, rl);
-            if (lane < SB) {
-                double *X = Dinv + (b / SB) * SB * PD;
+            if (r2 < T) {
 #pragma unroll
-                for (int r = 0; r < SB; ++r) X[r * PD + rl] = x[r];  // X[r][rl]; zero above the diagonal by construction
+                for (int c = 0; c < SB; ++c) D[r2][b + c] = a2[c];
             }
-        } else if (tid < below + 1) {
-            const int i = b + SB + tid;
-            double a[SB];
-#pragma unroll
-            for (int c = 0; c < SB; ++c) a[c] = D[i][b + c];
-            trsm_col<0>(a, D, dinvd, b);
-#pragma unroll
-            for (int c = 0; c < SB; ++c) D[i][b + c] = a[c];
+            if (tr && b == 0 && tid == 0) tr[11] = clock64();
+        } else if (b > 0) {
+            const int pb = b - SB;
+            if (warp == 1) {
+                rhs_row_step(D, dinvd, pb, false);
+            } else if (warp == 7) {
+                block_inverse(D, dinvd, Dinv, pb);
+            } else {  // warps 2..6: columns [b + 16, 64) from panel pb (the first 16 were done in phase 2)
+                const int f0 = (b + SB) / 8;
+                int f = 0;
+                for (int fr = f0; fr < T / 8; ++fr)
+                    for (int fc = f0; fc <= fr; ++fc, ++f)
+                        if (f % 5 == warp - 2) frag_update(D, pb, fr, fc);
+            }
         }
         __syncthreads();
         if (tr && b == 0 && tid == 0) tr[12] = clock64();
-        if (below > 0) {
-            // next 16 columns [b+16, b+32), rows [b+16, 64]
-            rank16_update(D, b, b + SB, b + SB, b + 2 * SB, tid, kThreads);
+        // ---- phase 2: columns [b + 16, b + 32), rows [b + 16, 64) from panel b — what the next panel needs
+        if (b + SB < T) {
+            const int f0 = (b + SB) / 8;
+            int f = 0;
+            for (int fc = f0; fc < f0 + 2; ++fc)
+                for (int fr = fc; fr < T / 8; ++fr, ++f)
+                    if ((f & 7) == warp) frag_update(D, b, fr, fc);
             __syncthreads();
         }
         if (tr && b == 0 && tid == 0) tr[13] = clock64();
     }
+    // tail: the last panel's block inverse and the right-hand side against it
+    if (warp == 1)
+        rhs_row_step(D, dinvd, T - SB, true);
+    else if (warp == 7)
+        block_inverse(D, dinvd, Dinv, T - SB);
+    __syncthreads();
     bad_out = bad;
 }
 
