@@ -234,12 +234,14 @@ int xrb_match_get(xrb_matcher *m, int max_match, uint32_t (*match_buffer)[2], fl
         cudaSuccess)
         return -1;
     if (launch_vlow(distmax, ratiomax, m->vlow.as<int>(), st)) return -1;
-    if (use_fused(m, std::max(n1, n2))) {
-        if (match_fused(m, m->pairdesc.as<PairDesc>(), 1, true, distmax, ratiomax, mutual_best_match, max_match,
-                        m->counts.as<int32_t>(), m->strided.as<uint32_t[2]>(), stride, st))
+    {
+        // ONE pair: the persistent tcgen05 kernels give a pair to one CTA (1/148 of the device, ~1.1 ms for
+        // 4096 x 4096); the tiled dp4a kernel spreads the same pair over (n1/128) x (n2/128) CTAs.  Same
+        // integer dot products, same top-2 state, same finalize: bit-identical lists.
+        Top2State rows{m->rows_best.as<unsigned long long>(), m->rows_second.as<unsigned int>()};
+        Top2State cols{m->cols_best.as<unsigned long long>(), m->cols_second.as<unsigned int>()};
+        if (launch_score_dp4a(m->pairdesc.as<PairDesc>(), 1, n1, n2, m->state_stride, rows, cols, m->vlow.as<int>(), st))
             return -1;
-    } else {
-        if (score(m, m->pairdesc.as<PairDesc>(), 1, n1, n2, st, true)) return -1;
         if (finalize(m, m->pairdesc.as<PairDesc>(), 1, distmax, ratiomax, mutual_best_match,
                      max_match, m->counts.as<int32_t>(), m->strided.as<uint32_t[2]>(), stride, st))
             return -1;
