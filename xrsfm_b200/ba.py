@@ -177,11 +177,11 @@ class BASolver:
         return keep[:n_obs], out[:n_pts], err[:n_pts], ang[:n_pts], (int(counts[0]), int(counts[1]))
 
     def profile_detail(self):
-        out = (C.c_double * 16)()
-        _lib.check(_lib.lib().xrb_ba_profile_detail(self._h, out, 16), "xrb_ba_profile_detail")
+        out = (C.c_double * 20)()
+        _lib.check(_lib.lib().xrb_ba_profile_detail(self._h, out, 20), "xrb_ba_profile_detail")
         keys = ("lin_ms", "gather_ms", "cam_blocks_ms", "solves", "n_blocks", "n_incidences", "nc", "half_bandwidth",
                 "parts", "tile_columns", "tiles", "tiles_original", "plan_flops", "depth_factor", "depth_backward",
-                "chains")
+                "chains", "schur_window_ctas", "schur_window_stride", "camera_span", "longest_track")
         return dict(zip(keys, list(out)))
 
     def comm_init(self, rank, world, broadcast_bytes):

@@ -60,6 +60,11 @@ struct xrb_ba_solver {
     int nc_true = 0, parts = 1;  // variable camera columns; independent interiors of the column order
     CholPlan plan;
     CholWorkspace chol_ws;
+    // fused windowed Schur complement (sequence-like scenes), see ba_kernels.cu section 2b
+    bool use_window = false;
+    WindowPlanDev win;
+    DevBuf d_anchor, d_win_pts, d_cta_ptr, d_cta_cam0, d_pS, d_pC, d_wstats;
+    int cam_span = 0, max_track = 0;
     DevBuf d_holes, d_pat;
     int n_holes = 0;
     int n_var_q = 0, n_var_t = 0, n_var_pts = 0, n_res_blocks = 0;
@@ -269,12 +274,61 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
     }
     s->cur = 0;
     lt.lap("state + intrinsics uploads");
-    // ---- Schur structure: per-observation records, block incidence lists
+    // ---- Schur structure: fused camera windows when every point sees a narrow range of cameras, else
+    // per-observation records + block incidence lists
     {
+        s->use_window = false;
         s->n_blocks = 0, s->n_inc = 0;
-        if ((rc = s->d_Tt.reserve(std::max<size_t>(1, 18 * (size_t)s->O_local) * 8))) return rc;
-        if ((rc = s->d_h.reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
         BAProblemDev pd = s->prob();
+        if ((rc = s->d_anchor.reserve(std::max<size_t>(1, (size_t)s->P_local) * 4))) return rc;
+        if ((rc = s->d_wstats.reserve(16))) return rc;
+        if ((rc = ba_launch_point_anchor(pd, s->d_anchor.as<int32_t>(), s->d_wstats.as<int32_t>(), st))) return rc;
+        int32_t wst[4] = {0, 0, 0, 0};
+        XRB_CUDA(cudaMemcpyAsync(wst, s->d_wstats.p, 16, cudaMemcpyDeviceToHost, st));
+        XRB_CUDA(cudaStreamSynchronize(st));
+        s->cam_span = wst[0], s->max_track = wst[1];
+        const char *schur_env = getenv("XRB_BA_SCHUR");
+        const bool want_window = !(schur_env && strcmp(schur_env, "gather") == 0);
+        if (want_window && s->P_local > 0 && C >= 2 * kWinCams && wst[0] <= kWinMaxSpan && wst[1] <= kWinMaxTrack && wst[2] == 0) {
+            const int stride = kWinCams - wst[0], n_win = (C + stride - 1) / stride;
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+            const int parts = std::max(1, std::min(8, (4 * sms + n_win - 1) / n_win));
+            const int n_ctas = n_win * parts;
+            // points by window (counting sort on the host: O(points), once per load), each window split evenly
+            std::vector<int32_t> anchor((size_t)s->P_local), cnt((size_t)n_win + 1, 0), pts((size_t)s->P_local);
+            XRB_CUDA(cudaMemcpyAsync(anchor.data(), s->d_anchor.p, anchor.size() * 4, cudaMemcpyDeviceToHost, st));
+            XRB_CUDA(cudaStreamSynchronize(st));
+            for (int p = 0; p < s->P_local; ++p) cnt[(size_t)anchor[p] / stride + 1]++;
+            for (int w = 0; w < n_win; ++w) cnt[w + 1] += cnt[w];
+            {
+                std::vector<int32_t> at(cnt.begin(), cnt.end() - 1);
+                for (int p = 0; p < s->P_local; ++p) pts[at[(size_t)anchor[p] / stride]++] = p;
+            }
+            std::vector<int32_t> cta_ptr((size_t)n_ctas + 1), cta_cam0((size_t)n_ctas);
+            for (int w = 0; w < n_win; ++w) {
+                const int64_t b = cnt[w], n = cnt[w + 1] - cnt[w];
+                for (int part = 0; part < parts; ++part) {
+                    cta_ptr[(size_t)w * parts + part] = (int32_t)(b + n * part / parts);
+                    cta_cam0[(size_t)w * parts + part] = w * stride;
+                }
+            }
+            cta_ptr[n_ctas] = s->P_local;
+            if ((rc = upload(s->d_win_pts, pts.data(), pts.size(), st))) return rc;
+            if ((rc = upload(s->d_cta_ptr, cta_ptr.data(), cta_ptr.size(), st))) return rc;
+            if ((rc = upload(s->d_cta_cam0, cta_cam0.data(), cta_cam0.size(), st))) return rc;
+            if ((rc = s->d_pS.reserve((size_t)n_ctas * kWinBlocks * 36 * 8))) return rc;
+            if ((rc = s->d_pC.reserve((size_t)n_ctas * kWinCams * 54 * 8))) return rc;
+            XRB_CUDA(cudaStreamSynchronize(st));  // the host vectors go out of scope
+            s->win.win_pts = s->d_win_pts.as<int32_t>(), s->win.cta_ptr = s->d_cta_ptr.as<int32_t>();
+            s->win.cta_cam0 = s->d_cta_cam0.as<int32_t>(), s->win.pS = s->d_pS.as<double>(), s->win.pC = s->d_pC.as<double>();
+            s->win.n_ctas = n_ctas, s->win.n_win = n_win, s->win.parts = parts, s->win.stride = stride;
+            s->use_window = true;
+        }
+        if (!s->use_window && (rc = s->d_Tt.reserve(std::max<size_t>(1, 18 * (size_t)s->O_local) * 8))) return rc;
+        if (s->use_window && (rc = s->d_Tt.reserve(8))) return rc;
+        if ((rc = s->d_h.reserve(std::max<size_t>(1, 3 * (size_t)s->P_local) * 8))) return rc;
+        pd = s->prob();
         if ((rc = ba_build_block_lists(pd, s->W, s->d_inc, s->d_blk_ptr, s->d_blk_cams, &s->n_blocks, &s->n_inc, st)))
             return rc;
         lt.lap("block lists (device)");
@@ -326,17 +380,25 @@ int compute_step(xrb_ba_solver *s, const BAConsts &k, double radius, cudaStream_
     // zero S, rhs, U, gc, scalE + slots (n2c untouched), scal2 + scalL
     XRB_CUDA(cudaMemsetAsync(s->d_E.p, 0, s->off_n2c * 8, st));
     XRB_CUDA(cudaMemsetAsync(s->d_scal.p, 0, 2 * SC_COUNT * 8, st));
-    if ((rc = ba_launch_lin(P, x, k, L, inv_radius, s->scalE(), st))) return rc;
-    ev[7].rec(st);
-    // the camera-major reduction reads the records but never S: it runs beside the gather
-    XRB_CUDA(cudaEventRecord(s->ev_fork, st));
-    XRB_CUDA(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
-    if ((rc = ba_launch_cam_blocks(P, x, k, L, s->side_stream))) return rc;
-    XRB_CUDA(cudaEventRecord(s->ev_join, s->side_stream));
-    if ((rc = ba_launch_gather(P, L, st))) return rc;
-    ev[8].rec(st);
-    XRB_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
-    s->launches[0] += 3;
+    if (s->use_window) {
+        // sequence-like scene: one fused kernel (+ two small reductions), no per-observation records
+        if ((rc = ba_launch_schur_window(P, x, k, L, inv_radius, s->scalE(), s->win, st))) return rc;
+        ev[7].rec(st);
+        ev[8].rec(st);
+        s->launches[0] += 3;
+    } else {
+        if ((rc = ba_launch_lin(P, x, k, L, inv_radius, s->scalE(), st))) return rc;
+        ev[7].rec(st);
+        // the camera-major reduction reads the records but never S: it runs beside the gather
+        XRB_CUDA(cudaEventRecord(s->ev_fork, st));
+        XRB_CUDA(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
+        if ((rc = ba_launch_cam_blocks(P, x, k, L, s->side_stream))) return rc;
+        XRB_CUDA(cudaEventRecord(s->ev_join, s->side_stream));
+        if ((rc = ba_launch_gather(P, L, st))) return rc;
+        ev[8].rec(st);
+        XRB_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+        s->launches[0] += 3;
+    }
     ev[1].rec(st);
     if (s->world > 1) {
         XRB_CUDA(cudaMemcpyAsync(s->slots() + s->rank, s->scalE() + SC_GRAD_MAX_PT, 8, cudaMemcpyDeviceToDevice, st));
@@ -680,7 +742,8 @@ void xrb_ba_destroy(xrb_ba_solver *s) {
                       &s->d_obs_cam, &s->d_obs_uv, &s->d_pt_var, &s->d_obs_orig, &s->d_E, &s->d_Vinv, &s->d_gp,
                       &s->d_sc, &s->d_sp, &s->d_linv, &s->d_yc, &s->d_step_p, &s->d_scal, &s->d_full,
                       &s->d_obs_pt, &s->d_cam_ptr, &s->d_cam_obs, &s->d_inc, &s->d_blk_ptr, &s->d_blk_cams,
-                      &s->d_Tt, &s->d_h, &s->d_holes, &s->d_pat};
+                      &s->d_Tt, &s->d_h, &s->d_holes, &s->d_pat, &s->d_anchor, &s->d_win_pts, &s->d_cta_ptr,
+                      &s->d_cta_cam0, &s->d_pS, &s->d_pC, &s->d_wstats};
     for (DevBuf *b : bufs) b->release();
     s->plan.release();
     s->chol_ws.release();
@@ -1004,6 +1067,7 @@ int xrb_ba_profile_detail(const xrb_ba_solver *s, double *out, int n) {
         out[8] = s->parts, out[9] = h.nt, out[10] = h.n_tiles, out[11] = h.n_tiles_orig, out[12] = h.flops;
         out[13] = h.depth_f, out[14] = h.depth_b, out[15] = h.n_chain_f;
     }
+    if (n >= 20) out[16] = s->use_window ? s->win.n_ctas : 0, out[17] = s->win.stride, out[18] = s->cam_span, out[19] = s->max_track;
     return XRB_OK;
 }
 

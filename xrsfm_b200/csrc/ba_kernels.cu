@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cfloat>
+#include <climits>
 
 #include "ba_kernels.cuh"
 
@@ -887,6 +888,379 @@ int ba_launch_residuals(const BAProblemDev &P, const BAStateDev &x, const BACons
                         const int32_t *obs_orig, double *out, cudaStream_t st) {
     if (P.n_obs_local > 0) {
         k_residuals<<<(P.n_obs_local + 255) / 256, 256, 0, st>>>(P, x, k, obs_orig, out);
+        XRB_LAUNCHED();
+    }
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+
+// =====================================================================================
+// 2b. Fused Schur complement for scenes whose points see a narrow range of cameras (a sequence:
+//     KITTI-shaped C4).  One kernel replaces k_lin + k_gather + k_cam_blocks and their 144-byte
+//     record per observation: a CTA owns a WINDOW of kWinCams consecutive cameras and the points
+//     whose first camera falls into the window's stride; everything those points contribute —
+//     the off-diagonal 6 x 6 blocks between window cameras, the cameras' diagonal blocks, gradient
+//     and right-hand side — is accumulated on chip (blocks in shared memory, camera sums in
+//     registers) and leaves once, as a partial window.  Per batch of <= 32 points:
+//       b   one thread per observation: residual, Jacobians, Huber (lin_obs)  -> shared memory
+//       c1  one thread per point: V + D^2 = Lc Lc^T, V^-1, h                  -> HBM (k_backsub reads them)
+//       c2  one thread per observation: T~ = W Lc^-T, e = r - JX h            -> shared memory
+//       d   a warp per window camera: U, sum T~T~^T, g, rhs; the camera's observations in batch order
+//       e   a warp per camera pair: S_ab -= T~_a T~_b^T over the points that see both, in batch order
+//     Windows overlap by the camera span of a point, and a window may be split over several CTAs:
+//     k_window_reduce_* add the partial windows in a fixed order.  No atomics on doubles anywhere: the
+//     result is bit-reproducible.
+// =====================================================================================
+constexpr int kWinThreads = 512, kWinPts = 32, kWinObs = 320, kWinRec = 40;
+// record (doubles): [0,18) T~ (after c2; JX sits in [34,40) until then) | [18,30) Jc | 30,31 r | 32,33 e | [34,40) JX
+constexpr int kWinSmemBytes = (kWinBlocks * 36 + kWinObs * kWinRec + kWinPts * 12) * 8 + kWinPts * kWinCams * 2 + 2 * kWinObs + 512;
+
+__device__ __forceinline__ int win_block(int li, int lj) { return li * (li - 1) / 2 + lj; }  // li > lj
+
+__global__ void __launch_bounds__(kWinThreads, 1)
+k_schur_window(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L, double inv_radius, double *__restrict__ scalars,
+               WindowPlanDev W) {
+    extern __shared__ __align__(16) unsigned char win_smem[];
+    double *Sacc = reinterpret_cast<double *>(win_smem);
+    double *rec = Sacc + kWinBlocks * 36;
+    double *ptab = rec + kWinObs * kWinRec;  // per batch point: l00 l10 l11 l20 l21 l22 h0 h1 h2 pvar
+    unsigned short *slot = reinterpret_cast<unsigned short *>(ptab + kWinPts * 12);  // [pt][cam] -> batch obs, 0xFFFF = none
+    unsigned char *cam_of = reinterpret_cast<unsigned char *>(slot + kWinPts * kWinCams);
+    unsigned char *pt_of = cam_of + kWinObs;
+    int *meta = reinterpret_cast<int *>(pt_of + kWinObs);  // [0] n_pts, [1] n_obs, [2] present mask, [4..36] pt ids, [40..73] obs offsets
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x, c0 = W.cta_cam0[cta];
+    const int p_begin = W.cta_ptr[cta], p_end = W.cta_ptr[cta + 1];
+    for (int i = tid; i < kWinBlocks * 36; i += kWinThreads) Sacc[i] = 0.0;
+    // camera sums: warp w owns window cameras w and w + 16; lane owns outputs lane and lane + 32 of the 54
+    double cacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    double gmax = 0.0;
+    bool fail = false;
+    for (int pos = p_begin; pos < p_end;) {
+        __syncthreads();
+        if (warp == 0) {  // batch: as many of the next 32 points as fit kWinObs observations
+            const bool in = pos + lane < p_end;
+            const int p = in ? W.win_pts[pos + lane] : 0;
+            const int kn = in ? P.pt_ptr[p + 1] - P.pt_ptr[p] : 0;
+            int incl = kn;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const bool take = in && incl <= kWinObs;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, take);
+            const int n_pts = __ffs(~m) - 1 < 0 ? 32 : __ffs(~m) - 1;  // leading run of takes
+            meta[4 + lane] = p, meta[40 + lane] = incl - kn;
+            if (lane == 0) meta[0] = n_pts, meta[2] = 0;
+            if (lane == n_pts - 1) meta[1] = incl, meta[40 + n_pts] = incl;
+        }
+        for (int i = tid; i < kWinPts * kWinCams; i += kWinThreads) slot[i] = 0xFFFFu;
+        __syncthreads();
+        const int n_pts = meta[0], n_obs = meta[1];
+        // ---- b: one thread per observation
+        if (tid < n_obs) {
+            int lp = 0;
+            for (int step = 16; step > 0; step >>= 1)
+                if (lp + step < n_pts && meta[40 + lp + step] <= tid) lp += step;
+            const int p = meta[4 + lp];
+            const int o = P.pt_ptr[p] + (tid - meta[40 + lp]);
+            const bool pvar = P.pt_var[p] != 0;
+            LinObs lo;
+            lin_obs(P, x, k, L, o, p, pvar, lo);
+            const int lc = P.obs_cam[o] - c0;
+            double *r = rec + tid * kWinRec;
+            if (lo.active) {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) r[18 + j] = lo.Jc[j];
+                r[30] = lo.r0, r[31] = lo.r1;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) r[34 + j] = lo.JX[j];
+            } else {
+#pragma unroll
+                for (int j = 18; j < kWinRec; ++j) r[j] = 0.0;
+            }
+            cam_of[tid] = (unsigned char)lc, pt_of[tid] = (unsigned char)lp;
+            slot[lp * kWinCams + lc] = (unsigned short)tid;
+            atomicOr(&meta[2], 1 << lc);
+        }
+        __syncthreads();
+        // ---- c1: one thread per point
+        if (tid < n_pts) {
+            const int p = meta[4 + tid];
+            const bool pvar = P.pt_var[p] != 0;
+            double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+            for (int t = meta[40 + tid]; t < meta[40 + tid + 1]; ++t) {
+                const double *J = rec + t * kWinRec + 34, r0 = rec[t * kWinRec + 30], r1 = rec[t * kWinRec + 31];
+                V[0] += J[0] * J[0] + J[3] * J[3], V[1] += J[0] * J[1] + J[3] * J[4];
+                V[2] += J[0] * J[2] + J[3] * J[5], V[3] += J[1] * J[1] + J[4] * J[4];
+                V[4] += J[1] * J[2] + J[4] * J[5], V[5] += J[2] * J[2] + J[5] * J[5];
+                g[0] += J[0] * r0 + J[3] * r1, g[1] += J[1] * r0 + J[4] * r1, g[2] += J[2] * r0 + J[5] * r1;
+            }
+            double l00 = 1, l10 = 0, l11 = 1, l20 = 0, l21 = 0, l22 = 1, h0 = 0, h1 = 0, h2 = 0;
+            if (pvar) {  // same arithmetic as k_lin
+                const double a = V[0] + fmin(fmax(V[0], 1e-6), 1e32) * inv_radius;
+                const double d = V[3] + fmin(fmax(V[3], 1e-6), 1e32) * inv_radius;
+                const double f = V[5] + fmin(fmax(V[5], 1e-6), 1e32) * inv_radius;
+                const double b = V[1], c = V[2], e = V[4];
+                l00 = sqrt(a), l10 = b / l00, l20 = c / l00;
+                const double t11 = d - l10 * l10;
+                l11 = sqrt(t11), l21 = (e - l20 * l10) / l11;
+                const double t22 = f - l20 * l20 - l21 * l21;
+                l22 = sqrt(t22);
+                if (!(a > 0.0) || !(t11 > 0.0) || !(t22 > 0.0) || !isfinite(l22)) fail = true;
+                const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+                const double m10 = -l10 * i00 * i11, m21 = -l21 * i11 * i22;
+                const double m20 = (l10 * l21 - l20 * l11) * i00 * i11 * i22;
+                double Vi[6];
+                Vi[0] = i00 * i00 + m10 * m10 + m20 * m20, Vi[1] = m10 * i11 + m20 * m21, Vi[2] = m20 * i22;
+                Vi[3] = i11 * i11 + m21 * m21, Vi[4] = m21 * i22, Vi[5] = i22 * i22;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) L.Vinv[6 * (size_t)p + j] = Vi[j];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) L.gp[3 * (size_t)p + j] = g[j];
+                h0 = Vi[0] * g[0] + Vi[1] * g[1] + Vi[2] * g[2];
+                h1 = Vi[1] * g[0] + Vi[3] * g[1] + Vi[4] * g[2];
+                h2 = Vi[2] * g[0] + Vi[4] * g[1] + Vi[5] * g[2];
+                const double *sp = L.sp + 3 * (size_t)p;
+                gmax = fmax(gmax, fmax(fabs(g[0] / sp[0]), fmax(fabs(g[1] / sp[1]), fabs(g[2] / sp[2]))));
+            }
+            L.h[3 * (size_t)p] = h0, L.h[3 * (size_t)p + 1] = h1, L.h[3 * (size_t)p + 2] = h2;
+            double *pt = ptab + tid * 12;
+            pt[0] = l00, pt[1] = l10, pt[2] = l11, pt[3] = l20, pt[4] = l21, pt[5] = l22, pt[6] = h0, pt[7] = h1, pt[8] = h2;
+            pt[9] = pvar ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        // ---- c2: one thread per observation: T~ = W Lc^-T, e = r - JX h
+        if (tid < n_obs) {
+            double *r = rec + tid * kWinRec;
+            const double *pt = ptab + pt_of[tid] * 12;
+            const double *Jc = r + 18, *JX = r + 34;
+            r[32] = r[30] - (JX[0] * pt[6] + JX[1] * pt[7] + JX[2] * pt[8]);
+            r[33] = r[31] - (JX[3] * pt[6] + JX[4] * pt[7] + JX[5] * pt[8]);
+            if (pt[9] != 0.0) {
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    const double w0 = Jc[a] * JX[0] + Jc[6 + a] * JX[3];
+                    const double w1 = Jc[a] * JX[1] + Jc[6 + a] * JX[4];
+                    const double w2 = Jc[a] * JX[2] + Jc[6 + a] * JX[5];
+                    const double t0 = w0 / pt[0];
+                    const double t1 = (w1 - pt[1] * t0) / pt[2];
+                    const double t2 = (w2 - pt[3] * t0 - pt[4] * t1) / pt[5];
+                    r[a * 3] = t0, r[a * 3 + 1] = t1, r[a * 3 + 2] = t2;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 18; ++j) r[j] = 0.0;
+            }
+        }
+        __syncthreads();
+        const unsigned present = (unsigned)meta[2];
+        // ---- d: camera sums, the camera's observations in batch order
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int lc = warp + 16 * cc;
+            if (lc >= kWinCams || !((present >> lc) & 1u)) continue;
+            for (int base = 0; base < n_obs; base += 32) {
+                unsigned m = __ballot_sync(0xFFFFFFFFu, base + lane < n_obs && cam_of[base + lane] == lc);
+                while (m) {
+                    const int t = base + __ffs(m) - 1;
+                    m &= m - 1;
+                    const double *r = rec + t * kWinRec;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int j = lane + 32 * u;
+                        if (j >= 54) break;
+                        double v;
+                        if (j < 42) {
+                            int w = j < 21 ? j : j - 21, a = 0;
+                            while (w >= a + 1) w -= a + 1, ++a;  // w-th lower entry -> (a, b = w)
+                            v = j < 21 ? r[18 + a] * r[18 + w] + r[24 + a] * r[24 + w]
+                                       : r[a * 3] * r[w * 3] + r[a * 3 + 1] * r[w * 3 + 1] + r[a * 3 + 2] * r[w * 3 + 2];
+                        } else if (j < 48) {
+                            v = r[18 + j - 42] * r[30] + r[24 + j - 42] * r[31];
+                        } else {
+                            v = r[18 + j - 48] * r[32] + r[24 + j - 48] * r[33];
+                        }
+                        cacc[cc][u] += v;
+                    }
+                }
+            }
+        }
+        // ---- e: camera pairs (li > lj), the points that see both in batch order
+        for (int bi = warp; bi < kWinBlocks; bi += kWinThreads / 32) {
+            int li = 1;
+            while ((li + 1) * li / 2 <= bi) ++li;  // bi = li (li - 1) / 2 + lj
+            const int lj = bi - li * (li - 1) / 2;
+            if (!((present >> li) & 1u) || !((present >> lj) & 1u)) continue;
+            const unsigned short si = lane < n_pts ? slot[lane * kWinCams + li] : 0xFFFFu;
+            const unsigned short sj = lane < n_pts ? slot[lane * kWinCams + lj] : 0xFFFFu;
+            unsigned m = __ballot_sync(0xFFFFFFFFu, si != 0xFFFFu && sj != 0xFFFFu);
+            if (!m) continue;
+            const int e0 = lane, e1 = lane + 32;  // outputs of this lane: (a, c) = (e / 6, e % 6)
+            double acc0 = 0.0, acc1 = 0.0;
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int ti = __shfl_sync(0xFFFFFFFFu, (int)si, src), tj = __shfl_sync(0xFFFFFFFFu, (int)sj, src);
+                const double *Ti = rec + ti * kWinRec, *Tj = rec + tj * kWinRec;
+                {
+                    const int a = e0 / 6, c = e0 % 6;
+                    acc0 += Ti[a * 3] * Tj[c * 3] + Ti[a * 3 + 1] * Tj[c * 3 + 1] + Ti[a * 3 + 2] * Tj[c * 3 + 2];
+                }
+                if (e1 < 36) {
+                    const int a = e1 / 6, c = e1 % 6;
+                    acc1 += Ti[a * 3] * Tj[c * 3] + Ti[a * 3 + 1] * Tj[c * 3 + 1] + Ti[a * 3 + 2] * Tj[c * 3 + 2];
+                }
+            }
+            Sacc[bi * 36 + e0] += acc0;
+            if (e1 < 36) Sacc[bi * 36 + e1] += acc1;
+        }
+        pos += n_pts;
+    }
+    __syncthreads();
+    // ---- flush the partial window
+    double *pS = W.pS + (size_t)cta * kWinBlocks * 36;
+    for (int i = tid; i < kWinBlocks * 36; i += kWinThreads) pS[i] = Sacc[i];
+    double *pC = W.pC + (size_t)cta * kWinCams * 54;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        const int lc = warp + 16 * cc;
+        if (lc >= kWinCams) continue;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (lane + 32 * u < 54) pC[lc * 54 + lane + 32 * u] = cacc[cc][u];
+    }
+    if (fail) scalars[SC_FAIL] = 1.0;
+    gmax = fmax(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, 16));
+    gmax = fmax(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, 8));
+    gmax = fmax(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, 4));
+    gmax = fmax(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, 2));
+    gmax = fmax(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, 1));
+    if (lane == 0 && gmax > 0.0) atomic_max_nonneg(&scalars[SC_GRAD_MAX_PT], gmax);
+}
+
+// windows (and their parts) that hold camera pair (hi, lo) / camera c: w in [ceil((hi - 23) / S), floor(lo / S)]
+__device__ __forceinline__ void window_range(const WindowPlanDev &W, int hi, int lo, int &w0, int &w1) {
+    const int t = hi - (kWinCams - 1);
+    w0 = t <= 0 ? 0 : (t + W.stride - 1) / W.stride;
+    w1 = min(lo / W.stride, W.n_win - 1);
+}
+
+// off-diagonal blocks of S: 8 lanes per structure block, partial windows added in (window, part) order
+__global__ void __launch_bounds__(256)
+k_window_reduce_blocks(BAProblemDev P, BALinSys L, WindowPlanDev W) {
+    const int sub = threadIdx.x & 7;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    if (b >= P.n_blocks) return;
+    const int2 cams = P.blk_cams[b];  // columns(x) > columns(y)
+    if (cams.x == cams.y) return;      // cannot occur on this path (no camera twice on one point)
+    const bool x_hi = cams.x > cams.y;
+    const int hi = x_hi ? cams.x : cams.y, lo = x_hi ? cams.y : cams.x;
+    int w0, w1;
+    window_range(W, hi, lo, w0, w1);
+    int ra[6], cb[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        ra[j] = P.colq[cams.x] >= 0 ? P.colq[cams.x] + j : -1, ra[3 + j] = P.colt[cams.x] >= 0 ? P.colt[cams.x] + j : -1;
+        cb[j] = P.colq[cams.y] >= 0 ? P.colq[cams.y] + j : -1, cb[3 + j] = P.colt[cams.y] >= 0 ? P.colt[cams.y] + j : -1;
+    }
+    for (int e = sub; e < 36; e += 8) {
+        const int a = e / 6, c = e % 6;  // entry (a of cams.x, c of cams.y)
+        if (ra[a] < 0 || cb[c] < 0) continue;
+        const int pe = x_hi ? a * 6 + c : c * 6 + a;  // the partial holds M(hi, lo): rows = hi's parameters
+        double v = 0.0;
+        for (int w = w0; w <= w1; ++w) {
+            const int bi = win_block(hi - w * W.stride, lo - w * W.stride);
+            for (int part = 0; part < W.parts; ++part)
+                v += W.pS[((size_t)(w * W.parts + part) * kWinBlocks + bi) * 36 + pe];
+        }
+        L.S[L.tm.at(ra[a], cb[c])] = -v;
+    }
+}
+
+// camera sums: one thread per (camera, output)
+__global__ void __launch_bounds__(256)
+k_window_reduce_cams(BAProblemDev P, BALinSys L, WindowPlanDev W) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = idx / 54, j = idx % 54;
+    if (c >= P.n_cams) return;
+    const int cq = P.colq[c], ct = P.colt[c];
+    if (cq < 0 && ct < 0) return;
+    int w0, w1;
+    window_range(W, c, c, w0, w1);
+    double v = 0.0;
+    for (int w = w0; w <= w1; ++w)
+        for (int part = 0; part < W.parts; ++part)
+            v += W.pC[((size_t)(w * W.parts + part) * kWinCams + (c - w * W.stride)) * 54 + j];
+    int cols[6];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) cols[q] = cq >= 0 ? cq + q : -1, cols[3 + q] = ct >= 0 ? ct + q : -1;
+    if (j < 42) {
+        int w = j < 21 ? j : j - 21, a = 0;
+        while (w >= a + 1) w -= a + 1, ++a;
+        if (cols[a] >= 0 && cols[w] >= 0) {
+            if (j < 21)
+                L.U[(size_t)cols[a] * 6 + w] = v;
+            else
+                L.Ud[(size_t)cols[a] * 6 + w] = v;
+        }
+    } else if (j < 48) {
+        if (cols[j - 42] >= 0) L.gc[cols[j - 42]] = v;
+    } else {
+        if (cols[j - 48] >= 0) L.rhs[cols[j - 48]] = v;
+    }
+}
+
+int ba_launch_schur_window(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k, const BALinSys &L, double inv_radius,
+                           double *scalars, const WindowPlanDev &W, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        XRB_CUDA(cudaFuncSetAttribute(k_schur_window, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmemBytes));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    if (W.n_ctas > 0) {
+        k_schur_window<<<W.n_ctas, kWinThreads, kWinSmemBytes, st>>>(P, x, k, L, inv_radius, scalars, W);
+        XRB_LAUNCHED();
+    }
+    if (P.n_blocks > 0) {
+        k_window_reduce_blocks<<<(unsigned)(((long long)P.n_blocks * 8 + 255) / 256), 256, 0, st>>>(P, L, W);
+        XRB_LAUNCHED();
+    }
+    if (P.n_cams > 0) {
+        k_window_reduce_cams<<<(unsigned)(((long long)P.n_cams * 54 + 255) / 256), 256, 0, st>>>(P, L, W);
+        XRB_LAUNCHED();
+    }
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
+// per local point: first camera (natural index), camera span, and whether the window path can take it
+// (<= kWinPts... observations per point bounded, no camera twice)
+__global__ void k_point_anchor(BAProblemDev P, int32_t *__restrict__ anchor, int32_t *__restrict__ stats) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_pts_local) return;
+    const int k0 = P.pt_ptr[p], k1 = P.pt_ptr[p + 1];
+    int lo = INT_MAX, hi = -1, dup = 0;
+    for (int a = k0; a < k1; ++a) {
+        const int c = P.obs_cam[a];
+        lo = min(lo, c), hi = max(hi, c);
+        for (int b = k0; b < a; ++b) dup |= P.obs_cam[b] == c;
+    }
+    anchor[p] = k1 > k0 ? lo : 0;
+    if (k1 > k0) {
+        atomicMax(&stats[0], hi - lo);
+        atomicMax(&stats[1], k1 - k0);
+        if (dup) atomicMax(&stats[2], 1);
+    }
+}
+
+int ba_launch_point_anchor(const BAProblemDev &P, int32_t *anchor, int32_t *stats, cudaStream_t st) {
+    XRB_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), st));
+    if (P.n_pts_local > 0) {
+        k_point_anchor<<<(P.n_pts_local + 127) / 128, 128, 0, st>>>(P, anchor, stats);
         XRB_LAUNCHED();
     }
     XRB_CUDA(cudaGetLastError());

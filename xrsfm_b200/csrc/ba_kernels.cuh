@@ -71,6 +71,17 @@ struct BALinSys {
     double *h;          // generation 2: per local point (V + D^2)^-1 g_p  (3 doubles)
 };
 
+// Fused Schur complement of sequence-like scenes (ba_kernels.cu §2b): windows of kWinCams consecutive
+// cameras, stride = kWinCams - (camera span of a point); every window split over `parts` CTAs.
+constexpr int kWinCams = 24, kWinBlocks = kWinCams * (kWinCams - 1) / 2, kWinMaxSpan = 16, kWinMaxTrack = 32;
+struct WindowPlanDev {
+    const int32_t *win_pts = nullptr;   // local point ids sorted by first camera
+    const int32_t *cta_ptr = nullptr;   // [n_ctas + 1] ranges into win_pts
+    const int32_t *cta_cam0 = nullptr;  // [n_ctas] first camera of the CTA's window
+    double *pS = nullptr, *pC = nullptr;  // partial windows: [n_ctas][kWinBlocks][36], [n_ctas][kWinCams][54]
+    int n_ctas = 0, n_win = 0, parts = 1, stride = 8;
+};
+
 // scalar slots (doubles) produced on the device, read by the host controller
 enum {
     SC_MODEL_CHANGE = 0,  // -(J s)^T (r + J s / 2)
@@ -94,6 +105,10 @@ int ba_launch_lin(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
 int ba_launch_gather(const BAProblemDev &P, const BALinSys &L, cudaStream_t st);
 int ba_launch_cam_blocks(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
                          const BALinSys &L, cudaStream_t st);
+int ba_launch_schur_window(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k, const BALinSys &L, double inv_radius,
+                           double *scalars, const WindowPlanDev &W, cudaStream_t st);
+// anchor[p] = first camera of local point p; stats[3] = max camera span, longest track, a camera twice on a point
+int ba_launch_point_anchor(const BAProblemDev &P, int32_t *anchor, int32_t *stats, cudaStream_t st);
 int ba_launch_cam_diag(const BAProblemDev &P, const BAStateDev &x, const BALinSys &L,
                        double inv_radius, double *scalars, cudaStream_t st);
 int ba_launch_backsub(const BAProblemDev &P, const BAStateDev &x, const BAStateDev &cand,
