@@ -393,23 +393,24 @@ def test_lba_windows_batched_equal_single_solves_and_oracle():
 
 
 def test_fused_window_schur_equals_gather_path_and_oracle(monkeypatch):
-    """Sequence-like scenes take the fused windowed Schur kernel (ba_kernels.cu 2b: no per-observation records);
-    the gather path (k_lin / k_gather / k_cam_blocks) forms the same reduced system in another summation order."""
+    """The fused windowed Schur kernel for sequence-like scenes (ba_kernels.cu 2b: no per-observation records;
+    opt-in with XRB_BA_SCHUR=window, it is the slower of the two at C4) against the default gather path
+    (k_lin / k_gather / k_cam_blocks), which forms the same reduced system in another summation order."""
     for n_cams, n_pts, k, seed in ((150, 6000, 8, 81), (400, 30000, 10, 82), (60, 900, 5, 83)):
         sc = synth.make_sequential_scene(n_cams, n_pts, k, seed)
         sc.pt_fixed[::7] = 1
         sc.cam_q_fixed[5] = 1                                 # a camera with only three columns
+        monkeypatch.setenv("XRB_BA_SCHUR", "window")
         win = sc.copy_state()
         s_win_solver = ba.BASolver()
         s_win = s_win_solver.solve_scene(win, **ol.KGBA)
         d = s_win_solver.profile_detail()
         assert d["schur_window_ctas"] > 0 and d["camera_span"] <= 16
-        monkeypatch.setenv("XRB_BA_SCHUR", "gather")
+        monkeypatch.delenv("XRB_BA_SCHUR")
         gat = sc.copy_state()
         s_gat_solver = ba.BASolver()
         s_gat = s_gat_solver.solve_scene(gat, **ol.KGBA)
         assert s_gat_solver.profile_detail()["schur_window_ctas"] == 0
-        monkeypatch.delenv("XRB_BA_SCHUR")
         assert s_win.n_iterations_logged == s_gat.n_iterations_logged
         for i in range(min(6, s_win.n_iterations_logged)):
             a, b = s_win.iterations[i], s_gat.iterations[i]
@@ -421,7 +422,8 @@ def test_fused_window_schur_equals_gather_path_and_oracle(monkeypatch):
             s_ref = ol.ba_solve(ref, ol.ba_options(**ol.KGBA))
             _compare_logs(s_win, s_ref, rel=1e-6)
             _compare_states(win, ref)
-    # a scene the window path must refuse: cameras all over the place
+    # a scene the window path must refuse even when asked for: cameras all over the place
+    monkeypatch.setenv("XRB_BA_SCHUR", "window")
     sph = ba.BASolver()
     sph.solve_scene(synth.make_scene("C1"), **ol.GBA_FAST)
     assert sph.profile_detail()["schur_window_ctas"] == 0

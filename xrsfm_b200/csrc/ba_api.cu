@@ -287,8 +287,10 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
         XRB_CUDA(cudaMemcpyAsync(wst, s->d_wstats.p, 16, cudaMemcpyDeviceToHost, st));
         XRB_CUDA(cudaStreamSynchronize(st));
         s->cam_span = wst[0], s->max_track = wst[1];
+        // opt-in (XRB_BA_SCHUR=window): at C4 the fused kernel runs 9.7 ms against 6.2 ms for the three gather-path
+        // kernels — its per-batch phases are latency-bound at 16 warps per SM
         const char *schur_env = getenv("XRB_BA_SCHUR");
-        const bool want_window = !(schur_env && strcmp(schur_env, "gather") == 0);
+        const bool want_window = schur_env && strcmp(schur_env, "window") == 0;
         if (want_window && s->P_local > 0 && C >= 2 * kWinCams && wst[0] <= kWinMaxSpan && wst[1] <= kWinMaxTrack && wst[2] == 0) {
             const int stride = kWinCams - wst[0], n_win = (C + stride - 1) / stride;
             int sms = 148;
@@ -299,11 +301,14 @@ int do_load(xrb_ba_solver *s, const xrb_ba_problem *P) {
             std::vector<int32_t> anchor((size_t)s->P_local), cnt((size_t)n_win + 1, 0), pts((size_t)s->P_local);
             XRB_CUDA(cudaMemcpyAsync(anchor.data(), s->d_anchor.p, anchor.size() * 4, cudaMemcpyDeviceToHost, st));
             XRB_CUDA(cudaStreamSynchronize(st));
-            for (int p = 0; p < s->P_local; ++p) cnt[(size_t)anchor[p] / stride + 1]++;
-            for (int w = 0; w < n_win; ++w) cnt[w + 1] += cnt[w];
+            // sorted by first camera (stable in the point id): the points of one batch then share their cameras,
+            // so a batch touches ~ (span + 1)^2 / 2 camera pairs instead of the whole window's
             {
-                std::vector<int32_t> at(cnt.begin(), cnt.end() - 1);
-                for (int p = 0; p < s->P_local; ++p) pts[at[(size_t)anchor[p] / stride]++] = p;
+                std::vector<int32_t> per_cam((size_t)C + 1, 0);
+                for (int p = 0; p < s->P_local; ++p) per_cam[(size_t)anchor[p] + 1]++;
+                for (int c = 0; c < C; ++c) per_cam[c + 1] += per_cam[c];
+                for (int w = 0; w <= n_win; ++w) cnt[w] = per_cam[std::min<int64_t>((int64_t)w * stride, C)];
+                for (int p = 0; p < s->P_local; ++p) pts[per_cam[anchor[p]]++] = p;
             }
             std::vector<int32_t> cta_ptr((size_t)n_ctas + 1), cta_cam0((size_t)n_ctas);
             for (int w = 0; w < n_win; ++w) {

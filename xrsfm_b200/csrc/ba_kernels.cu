@@ -935,6 +935,24 @@ k_schur_window(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L, double inv_
     for (int i = tid; i < kWinBlocks * 36; i += kWinThreads) Sacc[i] = 0.0;
     // camera sums: warp w owns window cameras w and w + 16; lane owns outputs lane and lane + 32 of the 54
     double cacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    int dx[2][3], dy[2][3];  // record offsets of the three products of outputs lane and lane + 32
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int j = lane + 32 * u;
+        int a = 0, w = j < 21 ? j : (j < 42 ? j - 21 : 0);
+        while (j < 42 && w >= a + 1) w -= a + 1, ++a;  // w-th lower entry -> (a, b = w)
+        if (j < 21) {            // U: Jc^T Jc
+            dx[u][0] = 18 + a, dy[u][0] = 18 + w, dx[u][1] = 24 + a, dy[u][1] = 24 + w, dx[u][2] = 34, dy[u][2] = 34;
+        } else if (j < 42) {     // sum T~ T~^T
+            dx[u][0] = 3 * a, dy[u][0] = 3 * w, dx[u][1] = 3 * a + 1, dy[u][1] = 3 * w + 1, dx[u][2] = 3 * a + 2, dy[u][2] = 3 * w + 2;
+        } else if (j < 48) {     // g_c = Jc^T r
+            dx[u][0] = 18 + j - 42, dy[u][0] = 30, dx[u][1] = 24 + j - 42, dy[u][1] = 31, dx[u][2] = 34, dy[u][2] = 34;
+        } else if (j < 54) {     // rhs = Jc^T (r - JX h)
+            dx[u][0] = 18 + j - 48, dy[u][0] = 32, dx[u][1] = 24 + j - 48, dy[u][1] = 33, dx[u][2] = 34, dy[u][2] = 34;
+        } else {
+            dx[u][0] = dx[u][1] = dx[u][2] = dy[u][0] = dy[u][1] = dy[u][2] = 34;
+        }
+    }
     double gmax = 0.0;
     bool fail = false;
     for (int pos = p_begin; pos < p_end;) {
@@ -1053,10 +1071,12 @@ k_schur_window(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L, double inv_
 #pragma unroll
                 for (int j = 0; j < 18; ++j) r[j] = 0.0;
             }
+            r[34] = 0.0;  // JX is spent: slot 34 is the zero operand of the camera sums below
         }
         __syncthreads();
         const unsigned present = (unsigned)meta[2];
-        // ---- d: camera sums, the camera's observations in batch order
+        // ---- d: camera sums, the camera's observations in batch order; every output is x1 y1 + x2 y2 + x3 y3 of
+        // record entries (operand table in registers, slot 34 = 0 where a term is missing): no divergence
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
             const int lc = warp + 16 * cc;
@@ -1067,27 +1087,13 @@ k_schur_window(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L, double inv_
                     const int t = base + __ffs(m) - 1;
                     m &= m - 1;
                     const double *r = rec + t * kWinRec;
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int j = lane + 32 * u;
-                        if (j >= 54) break;
-                        double v;
-                        if (j < 42) {
-                            int w = j < 21 ? j : j - 21, a = 0;
-                            while (w >= a + 1) w -= a + 1, ++a;  // w-th lower entry -> (a, b = w)
-                            v = j < 21 ? r[18 + a] * r[18 + w] + r[24 + a] * r[24 + w]
-                                       : r[a * 3] * r[w * 3] + r[a * 3 + 1] * r[w * 3 + 1] + r[a * 3 + 2] * r[w * 3 + 2];
-                        } else if (j < 48) {
-                            v = r[18 + j - 42] * r[30] + r[24 + j - 42] * r[31];
-                        } else {
-                            v = r[18 + j - 48] * r[32] + r[24 + j - 48] * r[33];
-                        }
-                        cacc[cc][u] += v;
-                    }
+                    cacc[cc][0] += r[dx[0][0]] * r[dy[0][0]] + r[dx[0][1]] * r[dy[0][1]] + r[dx[0][2]] * r[dy[0][2]];
+                    cacc[cc][1] += r[dx[1][0]] * r[dy[1][0]] + r[dx[1][1]] * r[dy[1][1]] + r[dx[1][2]] * r[dy[1][2]];
                 }
             }
         }
-        // ---- e: camera pairs (li > lj), the points that see both in batch order
+        // ---- e: camera pairs (li > lj), the points that see both in batch order; the two half-warps take
+        // alternate points (outputs l, l + 16, l + 32 of the 36 per lane l of a half), halves added at the end
         for (int bi = warp; bi < kWinBlocks; bi += kWinThreads / 32) {
             int li = 1;
             while ((li + 1) * li / 2 <= bi) ++li;  // bi = li (li - 1) / 2 + lj
@@ -1097,24 +1103,33 @@ k_schur_window(BAProblemDev P, BAStateDev x, BAConsts k, BALinSys L, double inv_
             const unsigned short sj = lane < n_pts ? slot[lane * kWinCams + lj] : 0xFFFFu;
             unsigned m = __ballot_sync(0xFFFFFFFFu, si != 0xFFFFu && sj != 0xFFFFu);
             if (!m) continue;
-            const int e0 = lane, e1 = lane + 32;  // outputs of this lane: (a, c) = (e / 6, e % 6)
-            double acc0 = 0.0, acc1 = 0.0;
+            const int half = lane >> 4, l = lane & 15;
+            double acc[3] = {0.0, 0.0, 0.0};
             while (m) {
-                const int src = __ffs(m) - 1;
+                const int s0 = __ffs(m) - 1;
                 m &= m - 1;
-                const int ti = __shfl_sync(0xFFFFFFFFu, (int)si, src), tj = __shfl_sync(0xFFFFFFFFu, (int)sj, src);
-                const double *Ti = rec + ti * kWinRec, *Tj = rec + tj * kWinRec;
-                {
-                    const int a = e0 / 6, c = e0 % 6;
-                    acc0 += Ti[a * 3] * Tj[c * 3] + Ti[a * 3 + 1] * Tj[c * 3 + 1] + Ti[a * 3 + 2] * Tj[c * 3 + 2];
-                }
-                if (e1 < 36) {
-                    const int a = e1 / 6, c = e1 % 6;
-                    acc1 += Ti[a * 3] * Tj[c * 3] + Ti[a * 3 + 1] * Tj[c * 3 + 1] + Ti[a * 3 + 2] * Tj[c * 3 + 2];
+                const int s1 = m ? __ffs(m) - 1 : -1;
+                m &= m - 1 < m ? m - 1 : 0u;  // drop the second bit if there is one
+                const int src = half == 0 ? s0 : s1;
+                const int ti = __shfl_sync(0xFFFFFFFFu, (int)si, src < 0 ? 0 : src);
+                const int tj = __shfl_sync(0xFFFFFFFFu, (int)sj, src < 0 ? 0 : src);
+                if (src >= 0) {
+                    const double *Ti = rec + ti * kWinRec, *Tj = rec + tj * kWinRec;
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int e = l + 16 * u;
+                        if (e < 36) {
+                            const int a = e / 6, c = e % 6;
+                            acc[u] += Ti[a * 3] * Tj[c * 3] + Ti[a * 3 + 1] * Tj[c * 3 + 1] + Ti[a * 3 + 2] * Tj[c * 3 + 2];
+                        }
+                    }
                 }
             }
-            Sacc[bi * 36 + e0] += acc0;
-            if (e1 < 36) Sacc[bi * 36 + e1] += acc1;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const double tot = acc[u] + __shfl_down_sync(0xFFFFFFFFu, acc[u], 16);
+                if (half == 0 && l + 16 * u < 36) Sacc[bi * 36 + l + 16 * u] += tot;
+            }
         }
         pos += n_pts;
     }
