@@ -427,3 +427,17 @@ def test_fused_window_schur_equals_gather_path_and_oracle(monkeypatch):
     sph = ba.BASolver()
     sph.solve_scene(synth.make_scene("C1"), **ol.GBA_FAST)
     assert sph.profile_detail()["schur_window_ctas"] == 0
+
+
+def test_c5_shaped_clustered_scene(solver):
+    """BASELINE config C5 (1DSfM-shaped: clusters of cameras, one camera model per image) at reduced size: the
+    reduced camera system is block sparse — dense per cluster, couplings between neighbours — so the plan keeps
+    only those tiles plus the fill; trajectory and state against the oracle."""
+    sc = synth.make_scene("C5", 0.06)   # 300 cameras in 3 clusters, 90k points
+    assert sc.n_intr == sc.n_cams and (sc.cam_intr == np.arange(sc.n_cams)).all()
+    got, ref, s_got, s_ref = _run_both(solver, sc, **ol.GBA_FAST)
+    _compare_logs(s_got, s_ref, rel=1e-6)
+    _compare_states(got, ref)
+    d = solver.profile_detail()
+    nt = int(d["tile_columns"])
+    assert d["tiles"] < nt * (nt + 1) // 2  # genuinely sparse: not every tile pair is coupled

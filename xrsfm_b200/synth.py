@@ -308,11 +308,79 @@ def make_sequential_scene(n_cams, n_pts, obs_per_pt, seed, intr=KITTI_SIMPLE_RAD
                          height, noise_px, outlier_frac, behind_frac, baseline=step)
 
 
+def make_clustered_scene(n_cams, n_pts, obs_per_pt, seed, cams_per_cluster=100, shared_frac=0.08,
+                         intr=KITTI_SIMPLE_RADIAL, noise_px=0.5, outlier_frac=0.02, behind_frac=1e-4,
+                         radius=10.0, half_extent=3.0, spacing=14.0, width=1241, height=376):
+    """C5 "1DSfM-shaped" unordered scene (rec_1dsfm sizing, src/rec_1dsfm.cc:21-55): cameras in clusters (a
+    landmark photographed from all around), dense covisibility inside a cluster, a fraction of the points
+    also seen from the neighbouring cluster, and ONE CAMERA MODEL PER IMAGE (internet photos: every frame
+    has its own intrinsics block, all constant in the reference's BA).  The reduced camera system is block
+    sparse: dense diagonal blocks per cluster, couplings between neighbours, fill from the elimination."""
+    rng = np.random.default_rng(seed)
+    n_cl = max(1, int(round(n_cams / cams_per_cluster)))
+    cpc = [n_cams // n_cl + (1 if i < n_cams % n_cl else 0) for i in range(n_cl)]
+    ppc = [n_pts // n_cl + (1 if i < n_pts % n_cl else 0) for i in range(n_cl)]
+    side = int(np.ceil(np.sqrt(n_cl)))
+    qs, ts, Rs, centres, X_all, oc, op = [], [], [], [], [], [], []
+    cam0, pt0 = 0, 0
+    cl_cams, cl_centre = [], []
+    for ci in range(n_cl):
+        ctr = np.array([(ci % side) * spacing, (ci // side) * spacing, 0.0])
+        nc_, np_ = cpc[ci], ppc[ci]
+        i = np.arange(nc_) + 0.5
+        phi = np.arccos(1 - 2 * i / nc_)
+        theta = np.pi * (1 + 5 ** 0.5) * i
+        cc = ctr + radius * np.stack([np.cos(theta) * np.sin(phi), np.sin(theta) * np.sin(phi), np.cos(phi)], axis=1)
+        for c in range(nc_):
+            q, t = look_at_pose(cc[c], ctr)
+            qs.append(q), ts.append(t), Rs.append(rotmat_from_quat(q))
+        centres.append(cc)
+        X = ctr + rng.uniform(-half_extent, half_extent, size=(np_, 3))
+        k = min(obs_per_pt, nc_)
+        n_sh = int(round(shared_frac * np_)) if n_cl > 1 else 0
+        # own cluster: k random cameras per point (every camera of the cluster sees the landmark volume)
+        pick = np.argsort(rng.random((np_, nc_)), axis=1)[:, :k]
+        oc.append((cam0 + pick).reshape(-1))
+        op.append(np.repeat(pt0 + np.arange(np_), k))
+        cl_cams.append((cam0, nc_)), cl_centre.append(ctr)
+        X_all.append(X)
+        if n_sh and ci > 0:  # the first n_sh points are also seen by 3 cameras of the previous cluster that face them
+            pc0, pnc = cl_cams[ci - 1]
+            prev_cc = centres[ci - 1]
+            facing = np.argsort(np.linalg.norm(prev_cc - ctr, axis=1))[: max(3, pnc // 4)]  # the far side looks this way
+            far = np.argsort(-np.linalg.norm(prev_cc - ctr, axis=1))[: max(3, pnc // 4)]
+            cand = far  # cameras on the far side of the previous cluster look through their landmark towards this one
+            sel = cand[np.argsort(rng.random((n_sh, len(cand))), axis=1)[:, :3]]
+            oc.append((pc0 + sel).reshape(-1))
+            op.append(np.repeat(pt0 + np.arange(n_sh), 3))
+            del facing
+        cam0 += nc_
+        pt0 += np_
+    centres = np.concatenate(centres)
+    X = np.concatenate(X_all)
+    obs_cam, obs_pt = np.concatenate(oc), np.concatenate(op)
+    # keep only observations in front of their camera
+    R = np.array(Rs)[obs_cam]
+    z = np.einsum("ij,ij->i", R[:, 2, :], X[obs_pt]) + np.array(ts)[obs_cam][:, 2]
+    keep = z > 0.5
+    obs_cam, obs_pt = obs_cam[keep], obs_pt[keep]
+    sc = _finish_scene(rng, Rs, qs, ts, centres, X, obs_cam, obs_pt, intr, width, height, noise_px, outlier_frac,
+                       behind_frac, baseline=np.sqrt(4 * np.pi * radius ** 2 / max(cpc)))
+    # one camera model per image
+    n_c = len(qs)
+    sc["intr"] = np.ascontiguousarray(np.repeat(sc["intr"], n_c, axis=0))
+    sc["intr_model"] = np.full(n_c, 2, dtype=np.int32)
+    sc["cam_intr"] = np.arange(n_c, dtype=np.int32)
+    sc["n_intr"] = n_c
+    return sc
+
+
 SCENES = {
     # name: (builder, n_cams, n_pts, obs_per_pt, seed index)
     "C1": (make_sphere_scene, 20, 2_000, 10, 0),
     "C2": (make_sphere_scene, 500, 200_000, 10, 1),
     "C4": (make_sequential_scene, 2_700, 1_000_000, 10, 3),
+    "C5": (make_clustered_scene, 5_000, 1_500_000, 8, 4),
 }
 
 
