@@ -140,6 +140,10 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // contiguous row-major 32 KB tile -> shared [64][PM] (16-byte copies on the L2 path)
@@ -281,18 +285,31 @@ __device__ __forceinline__ double rcp_nr(double d) {
     e = fma(-d, y, 1.0);
     return fma(y, e, y);
 }
+// 1 / sqrt(d) for a positive, finite, normal d: MUFU seed + one third-order step, no special-case branch —
+// the library rsqrt carries one, which ends the basic block and keeps the scheduler from interleaving this chain
+// with the reciprocal's (a single warp issues in order: chains it cannot interleave simply add up)
+__device__ __forceinline__ double rsqrt_nr(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double t = d * y;
+    const double e = fma(-t, y, 1.0);
+    const double q = fma(0.375, e, 0.5);
+    const double ye = y * e;
+    return fma(ye, q, y);
+}
 template <int J, int C>
-__device__ __forceinline__ void fac2_upd(double (&a1)[SB], double (&a2)[SB]) {
+__device__ __forceinline__ void fac2_upd(double (&a1)[SB], double (&a2)[SB], const double *col) {
     if constexpr (C < SB) {
-        const double lcj = __shfl_sync(0xFFFFFFFFu, a1[J], C);  // L[b + C][b + J]: the diagonal block's rows sit in lanes 0..15
+        const double lcj = col[C];  // L[b + C][b + J], one broadcast read (measured: a chain of 64-bit shuffles
+                                    // costs 27 cycles each and a single warp cannot overlap 30 of them per column)
         a1[C] = fma(-a1[J], lcj, a1[C]);
         a2[C] = fma(-a2[J], lcj, a2[C]);
-        fac2_upd<J, C + 1>(a1, a2);
+        fac2_upd<J, C + 1>(a1, a2, col);
     }
 }
 template <int J>
 __device__ __forceinline__ void fac2_col(double (&a1)[SB], double (&a2)[SB], const int lane, double d, double &inv_mine,
-                                         bool &bad) {
+                                         bool &bad, double *sc) {
     if constexpr (J < SB) {
         if (!(d > 0.0) || !isfinite(d)) bad = true, d = 1.0;
         double dnext = 1.0;
@@ -301,14 +318,17 @@ __device__ __forceinline__ void fac2_col(double (&a1)[SB], double (&a2)[SB], con
             const double dn = fma(-(a1[J] * a1[J]), rd, a1[J + 1]);  // meaningful on lane J + 1
             dnext = __shfl_sync(0xFFFFFFFFu, dn, J + 1);
         }
-        const double inv = rsqrt(d);
+        const double inv = rsqrt_nr(d);
         if (lane == J) inv_mine = inv;
         a1[J] *= inv, a2[J] *= inv;
-        fac2_upd<J, J + 1>(a1, a2);
+        double *col = sc + (J & 1) * SB;  // the scaled column of the diagonal block, double-buffered
+        if (lane < SB) col[lane] = a1[J];
+        __syncwarp();
+        fac2_upd<J, J + 1>(a1, a2, col);
         if constexpr (J + 1 < SB) {
             if (lane == J + 1) a1[J + 1] = dnext;  // one value for the pivot, the one its rsqrt sees
         }
-        fac2_col<J + 1>(a1, a2, lane, dnext, inv_mine, bad);
+        fac2_col<J + 1>(a1, a2, lane, dnext, inv_mine, bad, sc);
     }
 }
 
@@ -383,7 +403,7 @@ __device__ __forceinline__ void rhs_row_step(double (*D)[PA], const double *dinv
 // In-place Cholesky of the 64 x 64 tile in shared memory D (lower part); dinvd[64] receives
 // 1 / L[r][r], Dinv[4][16][PD] the inverses of the four 16 x 16 diagonal blocks of L.
 // Row 64 of D holds the right-hand side of this block column and leaves as y = L^-1 rhs.
-__device__ __forceinline__ void potrf64(double (*D)[PA], double *dinvd, double *Dinv, bool &bad_out, long long *tr = nullptr) {
+__device__ __forceinline__ void potrf64(double (*D)[PA], double *dinvd, double *Dinv, double *sc, bool &bad_out, long long *tr = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bool bad = false;
     for (int b = 0; b < T; b += SB) {
@@ -394,7 +414,7 @@ __device__ __forceinline__ void potrf64(double (*D)[PA], double *dinvd, double *
 #pragma unroll
             for (int c = 0; c < SB; ++c) a1[c] = r1 < T ? D[r1][b + c] : 0.0, a2[c] = r2 < T ? D[r2][b + c] : 0.0;
             double inv_mine = 1.0;
-            fac2_col<0>(a1, a2, lane, __shfl_sync(0xFFFFFFFFu, a1[0], 0), inv_mine, bad);
+            fac2_col<0>(a1, a2, lane, __shfl_sync(0xFFFFFFFFu, a1[0], 0), inv_mine, bad, sc);
             if (lane < SB) {
 #pragma unroll
                 for (int c = 0; c < SB; ++c)
@@ -523,30 +543,51 @@ __device__ __forceinline__ void run_chain(const CholArgs &A) {
                 if ((tid & 3) == 0) D[T][tid >> 2] -= s;
             }
             XRB_CLK(9)
-            double acc[2][4][2] = {};
-            gemm_nt(Bs, Bs, wm, acc);
-            XRB_CLK(10)
+            // diagonal update, lower fragments only: the 36 fragments (R, C <= R) are dealt round-robin, 5 or 4
+            // per warp — a warp issues one DMMA per ~32 cycles, so the busiest warp sets the time
+            {
+                const int wq = tid >> 5;
+                int fR[5], fC[5];
 #pragma unroll
-            for (int fr = 0; fr < 2; ++fr)
-#pragma unroll
-                for (int fc = 0; fc < 4; ++fc) {
-                    const int r = wm.r0 + 8 * fr + wm.g, c = wm.c0 + 8 * fc + 2 * wm.t;
-                    D[r][c] -= acc[fr][fc][0], D[r][c + 1] -= acc[fr][fc][1];
+                for (int i = 0; i < 5; ++i) {
+                    const int f = wq + 8 * i;
+                    int R = 0;
+                    while ((R + 1) * (R + 2) / 2 <= f) ++R;  // f = R (R + 1) / 2 + C
+                    fR[i] = f < 36 ? R : -1, fC[i] = f - R * (R + 1) / 2;
                 }
+                double acc[5][2];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) acc[i][0] = acc[i][1] = 0.0;
+                const double *base = Bs + wm.g * PM + wm.t;
+#pragma unroll 2
+                for (int p = 0; p < T; p += 4) {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i)
+                        if (fR[i] >= 0) dmma(acc[i], base[fR[i] * 8 * PM + p], base[fC[i] * 8 * PM + p]);
+                }
+                XRB_CLK(10)
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+                    if (fR[i] >= 0) {
+                        const int r = 8 * fR[i] + wm.g, c = 8 * fC[i] + 2 * wm.t;
+                        D[r][c] -= acc[i][0], D[r][c + 1] -= acc[i][1];
+                    }
+            }
             // the flag for L_k,kp goes out while the factorisation starts (its first barrier absorbs the fence)
             cta_publish_async(A.f.pdone() + s_kkp, 1);
         }
         XRB_CLK(3)
         bool bad = false;
-        potrf64(D, dinvd, Dinv, bad, tron && ft < 256 ? A.trace + ft * 16 : nullptr);
+        potrf64(D, dinvd, Dinv, sm + kOffVec + 4 * T, bad, tron && ft < 256 ? A.trace + ft * 16 : nullptr);
         any_bad |= bad;
         XRB_CLK(4)
         {
             double *dst = A.tiles + (size_t)s_kk * T * T;
-            for (int idx = tid; idx < T * T; idx += kThreads) {
-                const double v = D[idx >> 6][idx & 63];
-                dst[idx] = v;
-                Ls[(idx >> 6) * PM + (idx & 63)] = v;  // stays for the next diagonal tile of this chain
+            for (int idx = tid; idx < T * T / 2; idx += kThreads) {
+                const int r = idx >> 5, c = 2 * (idx & 31);
+                const double2 v = make_double2(D[r][c], D[r][c + 1]);
+                reinterpret_cast<double2 *>(dst)[idx] = v;
+                *reinterpret_cast<double2 *>(Ls + r * PM + c) = v;  // stays for the next diagonal tile of this chain
             }
             double *dd = A.dinv + (size_t)k * 4 * SB * SB;
             for (int idx = tid; idx < 4 * SB * SB; idx += kThreads) dd[idx] = Dinv[(idx >> 4) * PD + (idx & 15)];
@@ -703,22 +744,43 @@ __global__ void __launch_bounds__(kThreads, 1) k_tile_backsolve(CholArgs A) {
     double *const sm = g_sm;
     const int tid = threadIdx.x;
     __shared__ int task_s;
-    double *red = sm + kOffVec + 5 * T;  // [8][64]
+    double *red = sm + kOffVec + 5 * T;  // [8][64]  (workers; the chain places its own)
     if ((int)blockIdx.x < A.p.n_chain_b) {
-        double(*L)[PA] = reinterpret_cast<double(*)[PA]>(sm + kOffD);
-        double *Dinv = sm + kOffDinv0, *s = sm + kOffVec, *xk = s + T, *xs = s + 2 * T;  // xs[3][64]
-        for (;;) {
-            if (tid == 0) task_s = atomicAdd(A.f.next_b(), 1);
-            __syncthreads();
-            const int bt = task_s;
-            __syncthreads();
-            if (bt >= A.p.n_b) break;
-            const int4 r0 = __ldg(A.p.btasks + 3 * bt), r1 = __ldg(A.p.btasks + 3 * bt + 1), r2 = __ldg(A.p.btasks + 3 * bt + 2);
-            const int k = r0.x, s_kk = r0.y, n_near = r0.z, has_far = r0.w;
+        // the chain: L_kk and its block inverses of the NEXT column stream into the other buffer (cp.async)
+        // while this column is solved; the solve itself uses the whole CTA (matrix-vector steps per 16-block)
+        constexpr int PB = 66;  // pitch of L_kk here: rows stay 16-byte aligned for cp.async
+        double *Lbuf[2] = {sm, sm + T * PB};
+        double *Dbuf[2] = {sm + 2 * T * PB, sm + 2 * T * PB + kDinvSm};
+        double *vec = sm + 2 * T * PB + 2 * kDinvSm;  // s[64], xk[64], xs[3][64], red[8][64]
+        double *s = vec, *xk = vec + T, *xs = vec + 2 * T;
+        red = vec + 5 * T;
+        __shared__ TaskSlot slots[3];  // this column, the next one (complete), the one after (being claimed)
+        auto prefetch = [&](const TaskSlot &ts, int buf) {
+            const int k = ts.r[0].x, s_kk = ts.r[0].y;
+            const double *src = A.tiles + (size_t)s_kk * T * T;
+            for (int idx = tid; idx < T * T / 2; idx += kThreads) cp_async16(Lbuf[buf] + (idx >> 5) * PB + 2 * (idx & 31), src + 2 * idx);
+            const double *dsrc = A.dinv + (size_t)k * 4 * SB * SB;
+            for (int idx = tid; idx < 4 * SB * SB / 2; idx += kThreads) cp_async16(Dbuf[buf] + (idx >> 3) * PD + 2 * (idx & 7), dsrc + 2 * idx);
+            cp_async_commit();
+        };
+        if (tid == 0) {
+            claim_task(&slots[0], A.f.next_b(), A.p.btasks, A.p.n_b, 3);
+            claim_task(&slots[1], A.f.next_b(), A.p.btasks, A.p.n_b, 3);
+        }
+        __syncthreads();
+        if (slots[0].idx < A.p.n_b) prefetch(slots[0], 0);
+        for (int it = 0;; ++it) {
+            const int buf = it & 1;
+            const TaskSlot &cs = slots[it % 3], &ns = slots[(it + 1) % 3];
+            if (cs.idx >= A.p.n_b) break;
+            const int4 r0 = cs.r[0], r1 = cs.r[1], r2 = cs.r[2];
+            const int k = r0.x, n_near = r0.z, has_far = r0.w;
             const int row[3] = {r1.x, r1.y, r1.z}, slot[3] = {r2.x, r2.y, r2.z};
-            // everything that does not depend on the flags first: L_kk, its block inverses, the near tiles
-            tile_to_smem_padded(L, A.tiles + (size_t)s_kk * T * T);
-            dinv_to_smem(Dinv, A.dinv + (size_t)k * 4 * SB * SB);
+            // the claim of the column after next is spread over this step so that nobody waits for it
+            int claim_idx = 0;
+            int4 cr0 = make_int4(0, 0, 0, 0), cr1 = cr0, cr2 = cr0;
+            if (tid == kThreads - 1) claim_idx = atomicAdd(A.f.next_b(), 1);
+            // the near tiles do not depend on the flags either: request them before waiting
             TilePart tp[kNearTiles];
 #pragma unroll
             for (int a = 0; a < kNearTiles; ++a)
@@ -727,6 +789,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tile_backsolve(CholArgs A) {
                           n_near > 2 ? A.f.xdone() + row[2] : nullptr, 1, has_far ? A.f.wdone() + k : nullptr, 1,
                           A.f.abort_flag(), A.fail))
                 return;
+            if (tid == kThreads - 1 && claim_idx < A.p.n_b)
+                cr0 = __ldg(A.p.btasks + 3 * claim_idx), cr1 = __ldg(A.p.btasks + 3 * claim_idx + 1), cr2 = __ldg(A.p.btasks + 3 * claim_idx + 2);
+            const bool have_next = ns.idx < A.p.n_b;
+            if (have_next) prefetch(ns, buf ^ 1);
             if (tid < n_near * T) xs[tid] = __ldcg(A.wpart + A.p.nt * T + row[tid >> 6] * T + (tid & 63));
             __syncthreads();
             double s0 = 0.0, s1 = 0.0;
@@ -734,6 +800,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tile_backsolve(CholArgs A) {
             for (int a = 0; a < kNearTiles; ++a)
                 if (a < n_near) tile_rows_fma(tp[a], xs + a * T, s0, s1);
             part_store(red, s0, s1);
+            if (have_next) cp_async_wait_group<1>(); else cp_async_wait_group<0>();  // this column's L_kk has landed
             __syncthreads();
             if (tid < T) {
                 double v = __ldcg(A.rhs + k * T + tid) - part_sum(red, tid);
@@ -741,36 +808,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_tile_backsolve(CholArgs A) {
                 s[tid] = v;
             }
             __syncthreads();
-            // x_k = L_kk^-T s, 16-blocks bottom-up on warp 0: x[cb] = Dinv_cb^T (s[cb] - sum_{c' > cb} L[c'][cb]^T x[c'])
-            if (tid < 32) {
-                const int l = tid & 15;
-                for (int cb = T / SB - 1; cb >= 0; --cb) {
-                    const int col = cb * SB + l;
-                    double v0 = s[col], v1 = 0.0;
-                    for (int r = (cb + 1) * SB; r < T; r += 2) {
-                        v0 = fma(-L[r][col], xk[r], v0);
-                        v1 = fma(-L[r + 1][col], xk[r + 1], v1);
-                    }
-                    const double v = v0 + v1;
-                    const double *X = Dinv + cb * SB * PD;
-                    double o = 0.0;
+            // x_k = L_kk^-T s, 16-blocks bottom-up: x[cb] = Dinv_cb^T s[cb], then s[c] -= L[cb rows][c] x[cb] for c < 16 cb
+            const double *L = Lbuf[buf], *Dinv = Dbuf[buf];
+            for (int cb = T / SB - 1; cb >= 0; --cb) {
+                {
+                    const int l = tid >> 4, pp = tid & 15;  // output l, term pp
+                    double v = pp >= l ? Dinv[cb * SB * PD + pp * PD + l] * s[cb * SB + pp] : 0.0;
+                    v += __shfl_xor_sync(0xFFFFFFFFu, v, 8);
+                    v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+                    v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+                    v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+                    if (pp == 0) xk[cb * SB + l] = v;
+                }
+                __syncthreads();
+                if (cb > 0) {
+                    const int c = tid >> 2, q = tid & 3;  // column c, rows 4q .. 4q+3 of the block
+                    double v = 0.0;
+                    if (c < cb * SB) {
 #pragma unroll
-                    for (int p = 0; p < SB; ++p) {
-                        const double vp = __shfl_sync(0xFFFFFFFFu, v, p);
-                        if (p >= l) o = fma(X[p * PD + l], vp, o);  // (Dinv^T)[l][p] = Dinv[p][l]
+                        for (int j = 0; j < 4; ++j) v = fma(L[(cb * SB + 4 * q + j) * PB + c], xk[cb * SB + 4 * q + j], v);
                     }
-                    if (tid < SB) xk[col] = o;
-                    __syncwarp();
+                    v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+                    v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+                    if (q == 0 && c < cb * SB) s[c] -= v;
+                    __syncthreads();
                 }
             }
-            __syncthreads();
             if (tid < T) {
                 const double v = xk[tid];
                 A.x[k * T + tid] = v;
                 A.wpart[A.p.nt * T + k * T + tid] = v;  // x for the other CTAs
             }
-            cta_publish(A.f.xdone() + k, 1);
-            __syncthreads();
+            if (tid == kThreads - 1) {
+                TaskSlot &c2 = slots[(it + 2) % 3];
+                c2.idx = claim_idx, c2.r[0] = cr0, c2.r[1] = cr1, c2.r[2] = cr2;
+            }
+            cta_publish_async(A.f.xdone() + k, 1);
         }
         return;
     }
