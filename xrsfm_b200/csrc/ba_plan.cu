@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <numeric>
 
 #include "ba_plan.cuh"
@@ -94,17 +95,35 @@ void plan_column_order(const std::vector<int> &widths, int bw, bool allow_nd, st
             for (; v < V && acc < bw; ++v) part[v] = 2 * p + 1, acc += widths[v];
         }
     }
-    int cur = 0;
-    for (int pass = 0; pass < 2; ++pass)        // interiors first, then separators
-        for (int p = 0; p < P; ++p) {
-            const int id = 2 * p + pass;
-            bool any = false;
-            for (int v = 0; v < V; ++v) {
-                if (part[v] != id) continue;
-                if (!any) cur = round_up64(cur), any = true;
-                start[v] = cur, cur += widths[v];
+    // elimination order of the parts: interiors first (independent of each other), then the separators — which,
+    // once the interiors are gone, form a path (s_p is coupled to s_p+1 through interior p+1) — in odd-even
+    // (cyclic reduction) order: every other separator of the remaining path is independent of the others, so the
+    // separator system costs log2(P) levels instead of a chain of P - 1
+    std::vector<int> order;
+    for (int p = 0; p < P; ++p) order.push_back(2 * p);
+    {
+        std::vector<int> path;
+        for (int p = 0; p + 1 < P; ++p) path.push_back(p);
+        while (!path.empty()) {
+            std::vector<int> rest;
+            for (size_t i = 0; i < path.size(); ++i) {
+                if (i % 2 == 0)
+                    order.push_back(2 * path[i] + 1);
+                else
+                    rest.push_back(path[i]);
             }
+            path.swap(rest);
         }
+    }
+    int cur = 0;
+    for (const int id : order) {
+        bool any = false;
+        for (int v = 0; v < V; ++v) {
+            if (part[v] != id) continue;
+            if (!any) cur = round_up64(cur), any = true;
+            start[v] = cur, cur += widths[v];
+        }
+    }
     n_pad = std::max(64, round_up64(cur));
     parts = P;
 }
@@ -151,48 +170,119 @@ int build_chol_plan(int nt, const uint8_t *pat, CholPlanHost &H) {
     std::vector<int> kp(nt, -1);
     for (int k = 0; k < nt; ++k)
         for (int i : st[k]) kp[i] = k;
-    // ---- forward tasks with levels
+    // ---- forward tasks.  Sweep 1 walks the columns in order and sequences the updates of a tile by k (the
+    // natural order) to learn WHEN each update's operands are ready; the updates of a tile are then re-sequenced
+    // by that readiness (any fixed order is legal: an update never feeds the operands of another update of the
+    // same tile) — otherwise a separator tile that two interiors update would take the second interior's
+    // contributions only after all of the first's, although both run at the same time.  Sweep 2 computes the
+    // final longest-path levels for that sequencing.
     struct Rec {
         int32_t v[8];
     };
-    std::vector<Rec> F, Wt;
-    std::vector<int> levF(nt, 0), cnt(ns, 0), lastlev(ns, 0), pl(nt, 0);
+    struct UTask {
+        int i, j, k, s_ij, ready, seq, lev;
+    };
+    std::vector<UTask> U;
+    std::vector<std::vector<int>> upd_of(ns);  // tile -> its updates (ids into U), later in final order
     double flops = (double)nt * (64.0 * 64 * 64 / 3.0);
     const double t3 = 64.0 * 64 * 64;
-    for (int k = 0; k < nt; ++k) {
-        if (kp[k] < 0) {
-            levF[k] = 1;
-            F.push_back({{k, -1, slot(k, k), -1, -1, 0, 0, 1}});
-        }
-        const int s_kk = slot(k, k);
-        for (int i : st[k]) {
-            const int s_ik = slot(i, k);
-            if (kp[i] == k) {
-                const int s_ii = slot(i, i);
-                levF[i] = 1 + std::max(levF[k], std::max(lastlev[s_ik], lastlev[s_ii]));
-                F.push_back({{i, k, s_ii, s_ik, s_kk, cnt[s_ii], cnt[s_ik], levF[i]}});
-                pl[i] = levF[i];
-                flops += 2.0 * t3;  // substitution + diagonal update
-            } else {
-                const int lp = 1 + std::max(levF[k], lastlev[s_ik]);
-                Wt.push_back({{TASK_P, s_ik, s_kk, -1, cnt[s_ik], k, i, lp}});
-                pl[i] = lp;
-                flops += t3;
+    {
+        std::vector<int> levF(nt, 0), lastlev(ns, 0), pl(nt, 0);
+        for (int k = 0; k < nt; ++k) {
+            if (kp[k] < 0) levF[k] = 1;
+            for (int i : st[k]) {
+                const int s_ik = slot(i, k);
+                if (kp[i] == k) {
+                    levF[i] = 1 + std::max(levF[k], std::max(lastlev[s_ik], lastlev[slot(i, i)]));
+                    pl[i] = levF[i];
+                    flops += 2.0 * t3;  // substitution + diagonal update
+                } else {
+                    pl[i] = 1 + std::max(levF[k], lastlev[s_ik]);
+                    flops += t3;
+                }
             }
+            const std::vector<int> &S = st[k];
+            for (size_t a2 = 0; a2 < S.size(); ++a2)
+                for (size_t b2 = 0; b2 <= a2; ++b2) {
+                    const int i = S[a2], j = S[b2];
+                    if (i == j && kp[i] == k) continue;
+                    const int s_ij = slot(i, j);
+                    if (s_ij < 0) return XRB_ERR_INVALID;  // cannot happen: fill is closed under pair updates
+                    const int ready = 1 + std::max(pl[i], pl[j]);
+                    const int lev = std::max(ready, 1 + lastlev[s_ij]);
+                    upd_of[s_ij].push_back((int)U.size());
+                    U.push_back({i, j, k, s_ij, ready, 0, 0});
+                    lastlev[s_ij] = lev;
+                    flops += 2.0 * t3;
+                }
         }
-        const std::vector<int> &S = st[k];
-        for (size_t a = 0; a < S.size(); ++a)
-            for (size_t b = 0; b <= a; ++b) {
-                const int i = S[a], j = S[b];
-                if (i == j && kp[i] == k) continue;
-                const int s_ij = slot(i, j);
-                if (s_ij < 0) return XRB_ERR_INVALID;  // cannot happen: fill is closed under pair updates
-                const int lev = 1 + std::max(std::max(pl[i], pl[j]), lastlev[s_ij]);
-                Wt.push_back({{TASK_U, slot(i, k), slot(j, k), s_ij, cnt[s_ij], k, i, lev}});
-                cnt[s_ij]++, lastlev[s_ij] = lev;
-                flops += 2.0 * t3;
+    }
+    for (int sl = 0; sl < ns; ++sl) {
+        std::vector<int> &v = upd_of[sl];
+        std::stable_sort(v.begin(), v.end(), [&](int x, int y) { return U[x].ready != U[y].ready ? U[x].ready < U[y].ready : U[x].k < U[y].k; });
+        for (size_t q = 0; q < v.size(); ++q) U[v[q]].seq = (int)q;
+    }
+    // sweep 2: memoised longest path.  Dependencies always have a smaller level, so the recursion depth is
+    // bounded by the depth of the plan.
+    std::vector<int> levF(nt, 0), levP(ns, 0);
+    std::vector<signed char> stF(nt, 0), stP(ns, 0), stU(U.size(), 0);  // 0 new, 1 open, 2 done
+    bool cyclic = false;
+    struct Eval {
+        std::function<int(int)> F, P, Uf;
+    } ev;
+    auto last_upd_level = [&](int sl) { return upd_of[sl].empty() ? 0 : ev.Uf(upd_of[sl].back()); };
+    ev.F = [&](int k) -> int {
+        if (stF[k] == 2) return levF[k];
+        if (stF[k] == 1) { cyclic = true; return 0; }
+        stF[k] = 1;
+        int lev = last_upd_level(slot(k, k));
+        if (kp[k] >= 0) lev = std::max(lev, std::max(ev.F(kp[k]), last_upd_level(slot(k, kp[k]))));
+        levF[k] = lev + 1, stF[k] = 2;
+        return levF[k];
+    };
+    ev.P = [&](int sl_ik_k) -> int { return sl_ik_k; };  // placeholder, replaced below
+    std::vector<int> tile_i(ns, 0), tile_k(ns, 0);
+    for (int k = 0; k < nt; ++k) {
+        tile_i[slot(k, k)] = k, tile_k[slot(k, k)] = k;
+        for (int i : st[k]) tile_i[slot(i, k)] = i, tile_k[slot(i, k)] = k;
+    }
+    ev.P = [&](int sl) -> int {  // substitution of tile sl = (i, k), not merged
+        if (stP[sl] == 2) return levP[sl];
+        if (stP[sl] == 1) { cyclic = true; return 0; }
+        stP[sl] = 1;
+        const int lev = std::max(ev.F(tile_k[sl]), last_upd_level(sl));
+        levP[sl] = lev + 1, stP[sl] = 2;
+        return levP[sl];
+    };
+    auto producer = [&](int i, int k) { return kp[i] == k ? ev.F(i) : ev.P(slot(i, k)); };
+    ev.Uf = [&](int u) -> int {
+        if (stU[u] == 2) return U[u].lev;
+        if (stU[u] == 1) { cyclic = true; return 0; }
+        stU[u] = 1;
+        int lev = std::max(producer(U[u].i, U[u].k), producer(U[u].j, U[u].k));
+        if (U[u].seq > 0) lev = std::max(lev, ev.Uf(upd_of[U[u].s_ij][U[u].seq - 1]));
+        U[u].lev = lev + 1, stU[u] = 2;
+        return U[u].lev;
+    };
+    std::vector<Rec> F, Wt;
+    for (int k = 0; k < nt; ++k) {
+        const int lf = ev.F(k);
+        if (kp[k] < 0)
+            F.push_back({{k, -1, slot(k, k), -1, -1, (int)upd_of[slot(k, k)].size(), 0, lf}});
+        else
+            F.push_back({{k, kp[k], slot(k, k), slot(k, kp[k]), slot(kp[k], kp[k]), (int)upd_of[slot(k, k)].size(),
+                          (int)upd_of[slot(k, kp[k])].size(), lf}});
+        for (int i : st[k])
+            if (kp[i] != k) {
+                const int sl = slot(i, k);
+                Wt.push_back({{TASK_P, sl, slot(k, k), -1, (int)upd_of[sl].size(), k, i, ev.P(sl)}});
             }
     }
+    for (size_t u = 0; u < U.size(); ++u) {
+        const UTask &t = U[u];
+        Wt.push_back({{TASK_U, slot(t.i, t.k), slot(t.j, t.k), t.s_ij, t.seq, t.k, t.i, ev.Uf((int)u)}});
+    }
+    if (cyclic) return XRB_ERR_INVALID;
     std::stable_sort(F.begin(), F.end(), [](const Rec &a, const Rec &b) { return a.v[7] != b.v[7] ? a.v[7] < b.v[7] : a.v[0] < b.v[0]; });
     std::stable_sort(Wt.begin(), Wt.end(), [](const Rec &a, const Rec &b) {
         if (a.v[7] != b.v[7]) return a.v[7] < b.v[7];
