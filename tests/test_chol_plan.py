@@ -114,6 +114,9 @@ def simulate(pat, rng, n_workers=5):
         typ, s_ik, s_jk, s_ij, seq, k, i, _ = t
         if typ == 0:
             return upd[s_ik] >= seq and diag_done[k]
+        if typ == 2:  # fused P(i,k) + U(i,pk,k): the simulator runs it in one piece, so it needs everything
+            need, useq, s_pk_k = seq & 0xFFFF, seq >> 16, i
+            return upd[s_ik] >= need and diag_done[k] and pdone[s_pk_k] and upd[s_ij] >= useq
         return pdone[s_ik] and pdone[s_jk] and upd[s_ij] >= seq
 
     def execute(q, t):
@@ -136,6 +139,13 @@ def simulate(pat, rng, n_workers=5):
             assert upd[s_ik] == seq and not pdone[s_ik]
             tiles[s_ik] = np.linalg.solve(tiles[s_jk], tiles[s_ik].T).T
             pdone[s_ik] = 1
+        elif typ == 2:
+            need, useq, s_pk_k = seq & 0xFFFF, seq >> 16, i
+            assert upd[s_ik] == need and not pdone[s_ik] and upd[s_ij] == useq
+            tiles[s_ik] = np.linalg.solve(tiles[s_jk], tiles[s_ik].T).T   # s_jk holds the diagonal tile's slot
+            pdone[s_ik] = 1
+            tiles[s_ij] -= tiles[s_ik] @ tiles[s_pk_k].T
+            upd[s_ij] = useq + 1
         else:
             assert upd[s_ij] == seq, "updates must arrive in sequence"
             tiles[s_ij] -= tiles[s_ik] @ tiles[s_jk].T

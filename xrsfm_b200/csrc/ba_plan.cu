@@ -222,6 +222,16 @@ int build_chol_plan(int nt, const uint8_t *pat, CholPlanHost &H) {
         std::stable_sort(v.begin(), v.end(), [&](int x, int y) { return U[x].ready != U[y].ready ? U[x].ready < U[y].ready : U[x].k < U[y].k; });
         for (size_t q = 0; q < v.size(); ++q) U[v[q]].seq = (int)q;
     }
+    // Fused tasks PU(i, k) = P(i, k) followed, in the same CTA, by U(i, pk, k) with pk = parent(k) = the next column
+    // that meets row i: the row's fill then advances one task per column, like the chain, instead of two
+    // (substitution, then update) — in a dissected band every separator row is such a row.
+    std::vector<int> fused_u(ns, -1);            // tile (i, k) -> id of its fused update, or -1
+    std::vector<signed char> is_fused(U.size(), 0);
+    for (size_t u = 0; u < U.size(); ++u) {
+        const UTask &t = U[u];
+        const int pk = st[t.k][0];
+        if (t.j == pk && t.i > pk && kp[t.i] != t.k) fused_u[slot(t.i, t.k)] = (int)u, is_fused[u] = 1;
+    }
     // sweep 2: memoised longest path.  Dependencies always have a smaller level, so the recursion depth is
     // bounded by the depth of the plan.
     std::vector<int> levF(nt, 0), levP(ns, 0);
@@ -240,7 +250,7 @@ int build_chol_plan(int nt, const uint8_t *pat, CholPlanHost &H) {
         levF[k] = lev + 1, stF[k] = 2;
         return levF[k];
     };
-    ev.P = [&](int sl_ik_k) -> int { return sl_ik_k; };  // placeholder, replaced below
+    std::function<int(int, int)> producer;
     std::vector<int> tile_i(ns, 0), tile_k(ns, 0);
     for (int k = 0; k < nt; ++k) {
         tile_i[slot(k, k)] = k, tile_k[slot(k, k)] = k;
@@ -250,12 +260,18 @@ int build_chol_plan(int nt, const uint8_t *pat, CholPlanHost &H) {
         if (stP[sl] == 2) return levP[sl];
         if (stP[sl] == 1) { cyclic = true; return 0; }
         stP[sl] = 1;
-        const int lev = std::max(ev.F(tile_k[sl]), last_upd_level(sl));
+        int lev = std::max(ev.F(tile_k[sl]), last_upd_level(sl));
+        if (fused_u[sl] >= 0) {  // the fused update's own dependencies: the other panel tile, its predecessor in the tile
+            const UTask &t = U[fused_u[sl]];
+            lev = std::max(lev, producer(t.j, t.k));
+            if (t.seq > 0) lev = std::max(lev, ev.Uf(upd_of[t.s_ij][t.seq - 1]));
+        }
         levP[sl] = lev + 1, stP[sl] = 2;
         return levP[sl];
     };
-    auto producer = [&](int i, int k) { return kp[i] == k ? ev.F(i) : ev.P(slot(i, k)); };
+    producer = [&](int i, int k) { return kp[i] == k ? ev.F(i) : ev.P(slot(i, k)); };
     ev.Uf = [&](int u) -> int {
+        if (is_fused[u]) return U[u].lev = ev.P(slot(U[u].i, U[u].k));
         if (stU[u] == 2) return U[u].lev;
         if (stU[u] == 1) { cyclic = true; return 0; }
         stU[u] = 1;
@@ -275,12 +291,19 @@ int build_chol_plan(int nt, const uint8_t *pat, CholPlanHost &H) {
         for (int i : st[k])
             if (kp[i] != k) {
                 const int sl = slot(i, k);
-                Wt.push_back({{TASK_P, sl, slot(k, k), -1, (int)upd_of[sl].size(), k, i, ev.P(sl)}});
+                if (fused_u[sl] >= 0) {
+                    const UTask &t = U[fused_u[sl]];
+                    if (upd_of[sl].size() > 0xFFFF || t.seq > 0x7FFF) return XRB_ERR_INVALID;
+                    Wt.push_back({{TASK_PU, sl, slot(k, k), t.s_ij, (int)upd_of[sl].size() | (t.seq << 16), k, slot(t.j, k), ev.P(sl)}});
+                } else {
+                    Wt.push_back({{TASK_P, sl, slot(k, k), -1, (int)upd_of[sl].size(), k, i, ev.P(sl)}});
+                }
             }
     }
     for (size_t u = 0; u < U.size(); ++u) {
         const UTask &t = U[u];
-        Wt.push_back({{TASK_U, slot(t.i, t.k), slot(t.j, t.k), t.s_ij, t.seq, t.k, t.i, ev.Uf((int)u)}});
+        const int lev = ev.Uf((int)u);
+        if (!is_fused[u]) Wt.push_back({{TASK_U, slot(t.i, t.k), slot(t.j, t.k), t.s_ij, t.seq, t.k, t.i, lev}});
     }
     if (cyclic) return XRB_ERR_INVALID;
     std::stable_sort(F.begin(), F.end(), [](const Rec &a, const Rec &b) { return a.v[7] != b.v[7] ? a.v[7] < b.v[7] : a.v[0] < b.v[0]; });

@@ -42,11 +42,12 @@ struct TileMap {
 constexpr int kNearTiles = 3;   // tiles of a column the backward chain handles itself
 constexpr int kMaxChainCtas = 32;
 
-enum { TASK_P = 0, TASK_U = 1 };
+enum { TASK_P = 0, TASK_U = 1, TASK_PU = 2 };
 
 // records are int32[8] (two int4 loads)
 //   F : k, kp, s_kk, s_kkp, s_kpkp, need_kk, need_kkp, level
 //   W : type, s_ik, s_jk (P: s_kk), s_ij (P: unused), seq (P: need), k, i, level
+//       PU (fused P(i,k) + U(i,pk,k)): 2, s_ik, s_kk, s_ij = (i,pk), need | seq << 16, k, s_jk = (pk,k), level
 //   B : k, s_kk, n_near, has_far, row[3], level | slot[3], 0 ...   (int32[12])
 //   WB: k, far_begin, far_end, level
 struct CholPlanHost {

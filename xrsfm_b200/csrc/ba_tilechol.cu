@@ -12,8 +12,9 @@
 //          its shared memory; a dissected band runs one chain per interior at the same time.
 //   P(i,k) workers: L_ik = A_ik L_kk^-T, blocked substitution with the 16 x 16 diagonal-block inverses.
 //   U(i,j,k) workers: A_ij -= L_ik L_jk^T; the diagonal ones (i = j) also carry the forward substitution
-//          rhs_i -= L_ik y_k.  A tile receives its updates in increasing k (sequence numbers in the
+//          rhs_i -= L_ik y_k.  A tile receives its updates in a fixed order (sequence numbers in the
 //          flags): the factor is bit-reproducible, every rank of a multi-GPU solve gets the same one.
+//   PU(i,k) = P(i,k) fused with U(i,pk,k), pk the next column that meets row i (ba_plan.cu).
 // The tile products run on the FP64 tensor pipe (mma.sync.m8n8k4.f64, DMMA): operands in shared memory
 // with pitch 68 doubles (conflict-free fragment loads), 2 x 4 accumulator fragments per warp.
 // CTAs synchronise through release/acquire flags in global memory; the queues are sorted by longest-path
@@ -627,6 +628,52 @@ __device__ __forceinline__ bool run_task_P(const CholArgs &A, const int4 r0, con
     return true;
 }
 
+// PU(i, k): the substitution of tile (i, k) and, while L_ik is still in shared memory, the update of tile
+// (i, pk) with the panel tile of the next column pk that meets row i — the row's fill advances one task per column.
+__device__ __forceinline__ bool run_task_PU(const CholArgs &A, const int4 r0, const int4 r1, long long *wc) {
+    double *const sm = g_sm;
+    double *Bs = sm + kOffB, *Ls = sm + kOffL, *Dinv = sm + kOffDinv0;
+    const int s_ik = r0.y, s_kk = r0.z, s_ij = r0.w, need = r1.x & 0xFFFF, seq = r1.x >> 16, k = r1.y, s_jk = r1.z;
+    const WarpMap wm;
+    if (!cta_wait(A.f.upd() + s_ik, need, A.f.diag_done() + k, 1, nullptr, 0, nullptr, 0, A.f.abort_flag(), A.fail, wc))
+        return false;
+    tile_to_smem_async(Bs, A.tiles + (size_t)s_ik * T * T);
+    tile_to_smem_async(Ls, A.tiles + (size_t)s_kk * T * T);
+    cp_async_commit();
+    dinv_to_smem(Dinv, A.dinv + (size_t)k * 4 * SB * SB);
+    cp_async_wait_all();
+    __syncthreads();
+    trsm64(Bs, Ls, Dinv);
+    __syncthreads();
+    tile_from_smem(A.tiles + (size_t)s_ik * T * T, Bs);
+    cta_publish_async(A.f.pdone() + s_ik, 1);
+    // the update: Y = L_pk,k (published by the chain or a worker about now), C = tile (i, pk)
+    if (!cta_wait(A.f.pdone() + s_jk, 1, A.f.upd() + s_ij, seq, nullptr, 0, nullptr, 0, A.f.abort_flag(), A.fail, wc))
+        return false;
+    tile_to_smem_async(Ls, A.tiles + (size_t)s_jk * T * T);
+    cp_async_commit();
+    double *C = A.tiles + (size_t)s_ij * T * T;
+    double2 c[2][4];
+#pragma unroll
+    for (int fr = 0; fr < 2; ++fr)
+#pragma unroll
+        for (int fc = 0; fc < 4; ++fc)
+            c[fr][fc] = __ldcg(reinterpret_cast<const double2 *>(C + (wm.r0 + 8 * fr + wm.g) * T + wm.c0 + 8 * fc + 2 * wm.t));
+    cp_async_wait_all();
+    __syncthreads();
+    double acc[2][4][2] = {};
+    gemm_nt(Bs, Ls, wm, acc);
+#pragma unroll
+    for (int fr = 0; fr < 2; ++fr)
+#pragma unroll
+        for (int fc = 0; fc < 4; ++fc)
+            *reinterpret_cast<double2 *>(C + (wm.r0 + 8 * fr + wm.g) * T + wm.c0 + 8 * fc + 2 * wm.t) =
+                make_double2(c[fr][fc].x - acc[fr][fc][0], c[fr][fc].y - acc[fr][fc][1]);
+    cta_publish(A.f.upd() + s_ij, seq + 1);
+    __syncthreads();
+    return true;
+}
+
 __device__ __forceinline__ bool run_task_U(const CholArgs &A, const int4 r0, const int4 r1, long long *wc) {
     double *const sm = g_sm;
     const int tid = threadIdx.x;
@@ -689,7 +736,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tile_cholesky(CholArgs A) {
         __syncthreads();
         if (threadIdx.x == 0) claim_task(&slot_s, A.f.next_w(), A.p.wtasks, A.p.n_w, 2);  // read after this task's barriers
         const long long t0 = A.trace ? clock64() : 0;
-        const bool ok = r0.x == TASK_P ? run_task_P(A, r0, r1, wc) : run_task_U(A, r0, r1, wc);
+        const bool ok = r0.x == TASK_P ? run_task_P(A, r0, r1, wc)
+                        : r0.x == TASK_U ? run_task_U(A, r0, r1, wc) : run_task_PU(A, r0, r1, wc);
         if (A.trace) {
             if (r0.x == TASK_P) st_p += clock64() - t0, ++n_p; else st_u += clock64() - t0, ++n_u;
         }
