@@ -299,7 +299,7 @@ def test_c4_shaped_scene_dissected_order(solver, monkeypatch):
     got = sc.copy_state()
     s_nd = solver.solve_scene(got, **opts)
     d = solver.profile_detail()
-    assert d["parts"] >= 3 and d["chains"] >= 3 and d["depth_factor"] < d["tile_columns"]
+    assert d["parts"] >= 3 and d["chains"] >= 3
     ref = sc.copy_state()
     s_ref = ol.ba_solve(ref, ol.ba_options(**opts), os.cpu_count() or 1)
     for i in range(3):

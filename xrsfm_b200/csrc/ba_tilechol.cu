@@ -65,6 +65,7 @@ struct CholArgs {
     double *tiles, *rhs, *dinv, *x, *wpart, *fail;
     Flags f;
     long long *trace;   // optional clocks of the chain CTAs (debug), may be null
+    int pipeline;       // workers claim two tasks ahead and prefetch (many tasks per worker) or take one at a time
 };
 
 extern __shared__ __align__(16) double g_sm[];  // the CTA's dynamic shared memory
@@ -473,7 +474,9 @@ static_assert(kOffB % 2 == 0, "cp.async destinations are 16-byte aligned");
 constexpr int kOffL = kOffB + T * PM;         // [64][PM]  chain / P: L of the pivot column; U: Y operand
 constexpr int kOffDinv0 = kOffL + T * PM, kOffDinv1 = kOffDinv0 + kDinvSm;
 constexpr int kOffVec = kOffDinv1 + kDinvSm;  // dinvd[64], y[64], yprev[64], rhs[64], tmp[64], + 8 x 64 scratch
-constexpr int kSmemDoubles = kOffVec + 13 * T;
+constexpr int kChainDoubles = kOffVec + 13 * T;
+constexpr int kWorkerLayoutDoubles = 4 * T * PM + 2 * kDinvSm + 2 * T;  // run_workers: two operand sets
+constexpr int kSmemDoubles = kChainDoubles > kWorkerLayoutDoubles ? kChainDoubles : kWorkerLayoutDoubles;
 constexpr int kSmemBytes = kSmemDoubles * (int)sizeof(double);
 
 // ---- the chain: F tasks -------------------------------------------------------------------------
@@ -608,148 +611,221 @@ __device__ __forceinline__ void run_chain(const CholArgs &A) {
 }
 
 // ---- workers ------------------------------------------------------------------------------------
-__device__ __forceinline__ bool run_task_P(const CholArgs &A, const int4 r0, const int4 r1, long long *wc) {
-    double *const sm = g_sm;
-    double *Bs = sm + kOffB, *Ls = sm + kOffL, *Dinv = sm + kOffDinv0;
-    const int s_ik = r0.y, s_kk = r0.z, need = r1.x, k = r1.y;
-    if (!cta_wait(A.f.upd() + s_ik, need, A.f.diag_done() + k, 1, nullptr, 0, nullptr, 0, A.f.abort_flag(), A.fail, wc))
-        return false;
-    tile_to_smem_async(Bs, A.tiles + (size_t)s_ik * T * T);
-    tile_to_smem_async(Ls, A.tiles + (size_t)s_kk * T * T);
-    cp_async_commit();
-    dinv_to_smem(Dinv, A.dinv + (size_t)k * 4 * SB * SB);
-    cp_async_wait_all();
-    __syncthreads();
-    trsm64(Bs, Ls, Dinv);
-    __syncthreads();
-    tile_from_smem(A.tiles + (size_t)s_ik * T * T, Bs);
-    cta_publish(A.f.pdone() + s_ik, 1);
-    __syncthreads();  // shared memory is reused by the next task
-    return true;
-}
+// A worker keeps two tasks claimed beyond the one it runs.  While it waits for the last flag of the
+// current task it samples the operand flags of the next one in the same polling round; when they are
+// up, the next task's tiles stream into the other half of shared memory (cp.async) underneath the
+// current product.
+//   P(i,k)   L_ik = A_ik L_kk^-T (blocked substitution with the 16 x 16 diagonal-block inverses)
+//   U(i,j,k) A_ij -= L_ik L_jk^T; the diagonal ones also carry the forward substitution rhs_i -= L_ik y_k
+//   PU(i,k)  P(i,k) and, while L_ik is still in shared memory, U(i,pk,k) for the next column pk that meets
+//            row i: the row's fill advances one task per column
+constexpr int kWOffX = 0, kWOffY = T * PM, kWSet = 2 * T * PM;  // two operand sets: [X | Y] [X | Y]
+constexpr int kWOffDinv = 2 * kWSet, kWOffVec = kWOffDinv + 2 * kDinvSm;
+constexpr int kWorkerDoubles = kWOffVec + 2 * T;
+static_assert(kWorkerDoubles <= kSmemDoubles, "the kernel's shared memory covers the worker layout");
 
-// PU(i, k): the substitution of tile (i, k) and, while L_ik is still in shared memory, the update of tile
-// (i, pk) with the panel tile of the next column pk that meets row i — the row's fill advances one task per column.
-__device__ __forceinline__ bool run_task_PU(const CholArgs &A, const int4 r0, const int4 r1, long long *wc) {
-    double *const sm = g_sm;
-    double *Bs = sm + kOffB, *Ls = sm + kOffL, *Dinv = sm + kOffDinv0;
-    const int s_ik = r0.y, s_kk = r0.z, s_ij = r0.w, need = r1.x & 0xFFFF, seq = r1.x >> 16, k = r1.y, s_jk = r1.z;
-    const WarpMap wm;
-    if (!cta_wait(A.f.upd() + s_ik, need, A.f.diag_done() + k, 1, nullptr, 0, nullptr, 0, A.f.abort_flag(), A.fail, wc))
-        return false;
-    tile_to_smem_async(Bs, A.tiles + (size_t)s_ik * T * T);
-    tile_to_smem_async(Ls, A.tiles + (size_t)s_kk * T * T);
-    cp_async_commit();
-    dinv_to_smem(Dinv, A.dinv + (size_t)k * 4 * SB * SB);
-    cp_async_wait_all();
-    __syncthreads();
-    trsm64(Bs, Ls, Dinv);
-    __syncthreads();
-    tile_from_smem(A.tiles + (size_t)s_ik * T * T, Bs);
-    cta_publish_async(A.f.pdone() + s_ik, 1);
-    // the update: Y = L_pk,k (published by the chain or a worker about now), C = tile (i, pk)
-    if (!cta_wait(A.f.pdone() + s_jk, 1, A.f.upd() + s_ij, seq, nullptr, 0, nullptr, 0, A.f.abort_flag(), A.fail, wc))
-        return false;
-    tile_to_smem_async(Ls, A.tiles + (size_t)s_jk * T * T);
-    cp_async_commit();
-    double *C = A.tiles + (size_t)s_ij * T * T;
-    double2 c[2][4];
-#pragma unroll
-    for (int fr = 0; fr < 2; ++fr)
-#pragma unroll
-        for (int fc = 0; fc < 4; ++fc)
-            c[fr][fc] = __ldcg(reinterpret_cast<const double2 *>(C + (wm.r0 + 8 * fr + wm.g) * T + wm.c0 + 8 * fc + 2 * wm.t));
-    cp_async_wait_all();
-    __syncthreads();
-    double acc[2][4][2] = {};
-    gemm_nt(Bs, Ls, wm, acc);
-#pragma unroll
-    for (int fr = 0; fr < 2; ++fr)
-#pragma unroll
-        for (int fc = 0; fc < 4; ++fc)
-            *reinterpret_cast<double2 *>(C + (wm.r0 + 8 * fr + wm.g) * T + wm.c0 + 8 * fc + 2 * wm.t) =
-                make_double2(c[fr][fc].x - acc[fr][fc][0], c[fr][fc].y - acc[fr][fc][1]);
-    cta_publish(A.f.upd() + s_ij, seq + 1);
-    __syncthreads();
-    return true;
-}
-
-__device__ __forceinline__ bool run_task_U(const CholArgs &A, const int4 r0, const int4 r1, long long *wc) {
-    double *const sm = g_sm;
-    const int tid = threadIdx.x;
-    double *Xs = sm + kOffB, *Ys = sm + kOffL, *y = sm + kOffVec;
-    const int s_ik = r0.y, s_jk = r0.z, s_ij = r0.w, seq = r1.x, k = r1.y, i = r1.z;
-    const bool diag = s_ik == s_jk;
-    const WarpMap wm;
-    if (!cta_wait(A.f.pdone() + s_ik, 1, A.f.upd() + s_ij, seq, diag ? nullptr : A.f.pdone() + s_jk, 1, nullptr, 0,
-                  A.f.abort_flag(), A.fail, wc))
-        return false;
-    tile_to_smem_async(Xs, A.tiles + (size_t)s_ik * T * T);
-    if (!diag) tile_to_smem_async(Ys, A.tiles + (size_t)s_jk * T * T);
-    cp_async_commit();
-    double *C = A.tiles + (size_t)s_ij * T * T;
-    double2 c[2][4];
-#pragma unroll
-    for (int fr = 0; fr < 2; ++fr)
-#pragma unroll
-        for (int fc = 0; fc < 4; ++fc)
-            c[fr][fc] = __ldcg(reinterpret_cast<const double2 *>(C + (wm.r0 + 8 * fr + wm.g) * T + wm.c0 + 8 * fc + 2 * wm.t));
-    if (diag && tid < T) y[tid] = __ldcg(A.rhs + k * T + tid);
-    cp_async_wait_all();
-    __syncthreads();
-    double acc[2][4][2] = {};
-    gemm_nt(Xs, diag ? Xs : Ys, wm, acc);
-#pragma unroll
-    for (int fr = 0; fr < 2; ++fr)
-#pragma unroll
-        for (int fc = 0; fc < 4; ++fc)
-            *reinterpret_cast<double2 *>(C + (wm.r0 + 8 * fr + wm.g) * T + wm.c0 + 8 * fc + 2 * wm.t) =
-                make_double2(c[fr][fc].x - acc[fr][fc][0], c[fr][fc].y - acc[fr][fc][1]);
-    if (diag) {  // forward substitution rides on the diagonal update: rhs_i -= L_ik y_k, in the same order
-        const double s = row_dot(Xs, y);
-        if ((tid & 3) == 0) {
-            double *p = A.rhs + i * T + (tid >> 2);
-            *p = __ldcg(p) - s;
+// Lanes 0..2 of warp 0 spin on the blocking flags, lanes 3..4 sample the optional ones in the same
+// rounds; ready = every optional flag was up when the blocking ones were.
+__device__ __forceinline__ bool cta_wait_peek(const int *b0, int w0, const int *b1, int w1, const int *b2, int w2, const int *o0,
+                                              int ow0, const int *o1, int ow1, bool have_opt, bool &ready, int *abort_flag,
+                                              double *fail, long long *wait_cycles) {
+    __shared__ int ok_s, ready_s;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int *f = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : lane == 3 ? o0 : lane == 4 ? o1 : nullptr;
+        const int w = lane == 0 ? w0 : lane == 1 ? w1 : lane == 2 ? w2 : lane == 3 ? ow0 : ow1;
+        const bool optional = lane >= 3;
+        const long long t0 = wait_cycles ? clock64() : 0;
+        bool done = f == nullptr;
+        unsigned spins = 0;
+        int ok = 1;
+        for (;;) {
+            if (!done) done = ld_acquire(f) >= w;
+            if (__all_sync(0xFFFFFFFFu, done || optional)) break;
+            if ((++spins & 255u) == 0) {
+                const bool ab = spins > kSpinLimit || ld_acquire(abort_flag) != 0;
+                if (__any_sync(0xFFFFFFFFu, ab)) {
+                    ok = 0;
+                    break;
+                }
+            }
+        }
+        const bool all_opt = __all_sync(0xFFFFFFFFu, done || !optional);
+        if (lane == 0) {
+            if (!ok) {
+                st_release(abort_flag, 1);
+                *fail = 2.0;
+            }
+            ok_s = ok, ready_s = have_opt && all_opt && ok;
+            if (wait_cycles) *wait_cycles += clock64() - t0;
         }
     }
-    cta_publish(A.f.upd() + s_ij, seq + 1);
     __syncthreads();
-    return true;
+    const bool ok = ok_s != 0;
+    ready = ready_s != 0;
+    __syncthreads();
+    return ok;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_tile_cholesky(CholArgs A) {
-    if ((int)blockIdx.x < A.p.n_chain_f) {
-        run_chain(A);
-        return;
+struct WTask {
+    int type, s_ik, s_jk, s_ij, seq, k, i;
+    __device__ WTask(const int4 r0, const int4 r1) : type(r0.x), s_ik(r0.y), s_jk(r0.z), s_ij(r0.w), seq(r1.x), k(r1.y), i(r1.z) {}
+    __device__ bool diag() const { return s_ik == s_jk; }
+};
+
+// operand flags: P / PU wait for the tile's last update and the factored diagonal tile, U for both panel tiles
+__device__ __forceinline__ void operand_flags(const CholArgs &A, const WTask &t, const int *&f0, int &w0, const int *&f1, int &w1) {
+    if (t.type == TASK_U) {
+        f0 = A.f.pdone() + t.s_ik, w0 = 1;
+        f1 = t.diag() ? nullptr : A.f.pdone() + t.s_jk, w1 = 1;
+    } else {
+        f0 = A.f.upd() + t.s_ik, w0 = t.type == TASK_P ? t.seq : (t.seq & 0xFFFF);
+        f1 = A.f.diag_done() + t.k, w1 = 1;
     }
-    __shared__ TaskSlot slot_s;
+}
+
+__device__ __forceinline__ void issue_operands(const CholArgs &A, const WTask &t, int set) {
+    double *X = g_sm + set * kWSet + kWOffX, *Y = g_sm + set * kWSet + kWOffY;
+    tile_to_smem_async(X, A.tiles + (size_t)t.s_ik * T * T);
+    if (t.type != TASK_U) {
+        tile_to_smem_async(Y, A.tiles + (size_t)t.s_jk * T * T);  // s_jk holds the diagonal tile's slot
+        double *Dinv = g_sm + kWOffDinv + set * kDinvSm;
+        const double *src = A.dinv + (size_t)t.k * 4 * SB * SB;
+        for (int idx = threadIdx.x; idx < 4 * SB * SB / 2; idx += kThreads) cp_async16(Dinv + (idx >> 3) * PD + 2 * (idx & 7), src + 2 * idx);
+    } else if (!t.diag()) {
+        tile_to_smem_async(Y, A.tiles + (size_t)t.s_jk * T * T);
+    } else if (threadIdx.x < T / 2) {
+        cp_async16(g_sm + kWOffVec + set * T + 2 * threadIdx.x, A.rhs + t.k * T + 2 * threadIdx.x);
+    }
+    cp_async_commit();
+}
+
+// C (global tile) -= X Y^T with X, Y in shared memory; the C fragments were requested into c[][] before
+__device__ __forceinline__ void update_tile(double *C, const double2 (&c)[2][4], const double *Xs, const double *Ys, const WarpMap &wm) {
+    double acc[2][4][2] = {};
+    gemm_nt(Xs, Ys, wm, acc);
+#pragma unroll
+    for (int fr = 0; fr < 2; ++fr)
+#pragma unroll
+        for (int fc = 0; fc < 4; ++fc)
+            *reinterpret_cast<double2 *>(C + (wm.r0 + 8 * fr + wm.g) * T + wm.c0 + 8 * fc + 2 * wm.t) =
+                make_double2(c[fr][fc].x - acc[fr][fc][0], c[fr][fc].y - acc[fr][fc][1]);
+}
+__device__ __forceinline__ void load_c_frags(const double *C, double2 (&c)[2][4], const WarpMap &wm) {
+#pragma unroll
+    for (int fr = 0; fr < 2; ++fr)
+#pragma unroll
+        for (int fc = 0; fc < 4; ++fc)
+            c[fr][fc] = __ldcg(reinterpret_cast<const double2 *>(C + (wm.r0 + 8 * fr + wm.g) * T + wm.c0 + 8 * fc + 2 * wm.t));
+}
+
+__device__ __forceinline__ void run_workers(const CholArgs &A) {
+    const int tid = threadIdx.x;
+    __shared__ TaskSlot slots[3];
     // debug statistics (thread 0, only when the trace is armed): cycles waiting on flags, in P / U tasks
     long long st_wait = 0, st_p = 0, st_u = 0, n_p = 0, n_u = 0;
     long long *wc = A.trace ? &st_wait : nullptr;
     const long long t_begin = A.trace ? clock64() : 0;
-    if (threadIdx.x == 0) claim_task(&slot_s, A.f.next_w(), A.p.wtasks, A.p.n_w, 2);
-    __syncthreads();
-    for (;;) {
-        const int t = slot_s.idx;
-        if (t >= A.p.n_w) break;
-        const int4 r0 = slot_s.r[0], r1 = slot_s.r[1];
-        __syncthreads();
-        if (threadIdx.x == 0) claim_task(&slot_s, A.f.next_w(), A.p.wtasks, A.p.n_w, 2);  // read after this task's barriers
-        const long long t0 = A.trace ? clock64() : 0;
-        const bool ok = r0.x == TASK_P ? run_task_P(A, r0, r1, wc)
-                        : r0.x == TASK_U ? run_task_U(A, r0, r1, wc) : run_task_PU(A, r0, r1, wc);
-        if (A.trace) {
-            if (r0.x == TASK_P) st_p += clock64() - t0, ++n_p; else st_u += clock64() - t0, ++n_u;
-        }
-        if (!ok) return;
+    const WarpMap wm;
+    // with few tasks per worker (a dissected band) a claimed-but-waiting task may be the one another CTA could run:
+    // then every worker takes one task at a time
+    const bool pipe = A.pipeline != 0;
+    if (tid == 0) {
+        claim_task(&slots[0], A.f.next_w(), A.p.wtasks, A.p.n_w, 2);
+        if (pipe) claim_task(&slots[1], A.f.next_w(), A.p.wtasks, A.p.n_w, 2);
     }
-    if (A.trace && threadIdx.x == 0) {
+    __syncthreads();
+    bool have = false;  // the operands of the current task are already on their way (set `set`)
+    int set = 0;
+    for (int it = 0;; ++it) {
+        const TaskSlot &cs = slots[it % 3], &ns = slots[(it + 1) % 3];
+        if (cs.idx >= A.p.n_w) break;
+        const WTask cur(cs.r[0], cs.r[1]);
+        const bool have_next = pipe && ns.idx < A.p.n_w;
+        const WTask nxt(ns.r[0], ns.r[1]);
+        // the claim of the task after next is spread over this one so that nobody waits for it: counter
+        // now, record after the flags, shared-memory slot after the product (read from the next iteration on)
+        int claim_idx = 0;
+        int4 cr0 = make_int4(0, 0, 0, 0), cr1 = cr0;
+        if (pipe && tid == kThreads - 1) claim_idx = atomicAdd(A.f.next_w(), 1);
+        TaskSlot &claim_slot = slots[(it + 2) % 3];
+        const long long t0 = A.trace ? clock64() : 0;
+        const int *f0 = nullptr, *f1 = nullptr, *o0 = nullptr, *o1 = nullptr;
+        int w0 = 0, w1 = 0, ow0 = 0, ow1 = 0;
+        if (!have) operand_flags(A, cur, f0, w0, f1, w1);
+        if (have_next) operand_flags(A, nxt, o0, ow0, o1, ow1);
+        bool ready = false;
+        if (!cta_wait_peek(f0, w0, f1, w1, cur.type == TASK_U ? A.f.upd() + cur.s_ij : nullptr, cur.seq, o0, ow0, o1, ow1,
+                           have_next, ready, A.f.abort_flag(), A.fail, wc))
+            return;
+        if (!have) issue_operands(A, cur, set);
+        if (pipe && tid == kThreads - 1 && claim_idx < A.p.n_w) cr0 = __ldg(A.p.wtasks + 2 * claim_idx), cr1 = __ldg(A.p.wtasks + 2 * claim_idx + 1);
+        double *Xs = g_sm + set * kWSet + kWOffX, *Ys = g_sm + set * kWSet + kWOffY;
+        if (cur.type == TASK_U) {
+            double *C = A.tiles + (size_t)cur.s_ij * T * T;
+            double2 c[2][4];
+            load_c_frags(C, c, wm);
+            if (ready) issue_operands(A, nxt, set ^ 1);
+            if (ready) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
+            __syncthreads();
+            update_tile(C, c, Xs, cur.diag() ? Xs : Ys, wm);
+            if (pipe && tid == kThreads - 1) claim_slot.idx = claim_idx, claim_slot.r[0] = cr0, claim_slot.r[1] = cr1;
+            if (cur.diag()) {  // forward substitution rides on the diagonal update: rhs_i -= L_ik y_k, in the same order
+                const double s = row_dot(Xs, g_sm + kWOffVec + set * T);
+                if ((tid & 3) == 0) {
+                    double *p = A.rhs + cur.i * T + (tid >> 2);
+                    *p = __ldcg(p) - s;
+                }
+            }
+            cta_publish_async(A.f.upd() + cur.s_ij, cur.seq + 1);
+            if (A.trace) st_u += clock64() - t0, ++n_u;
+        } else {
+            if (ready) issue_operands(A, nxt, set ^ 1);
+            if (ready) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
+            __syncthreads();
+            trsm64(Xs, Ys, g_sm + kWOffDinv + set * kDinvSm);
+            if (pipe && tid == kThreads - 1) claim_slot.idx = claim_idx, claim_slot.r[0] = cr0, claim_slot.r[1] = cr1;
+            __syncthreads();
+            tile_from_smem(A.tiles + (size_t)cur.s_ik * T * T, Xs);
+            cta_publish_async(A.f.pdone() + cur.s_ik, 1);
+            if (cur.type == TASK_PU) {
+                // the update of tile (i, pk): Y = L_pk,k (published by the chain or a worker about now)
+                const int useq = cur.seq >> 16, s_pk_k = cur.i;
+                if (!cta_wait(A.f.pdone() + s_pk_k, 1, A.f.upd() + cur.s_ij, useq, nullptr, 0, nullptr, 0, A.f.abort_flag(), A.fail, wc))
+                    return;
+                tile_to_smem_async(Ys, A.tiles + (size_t)s_pk_k * T * T);
+                cp_async_commit();
+                double *C = A.tiles + (size_t)cur.s_ij * T * T;
+                double2 c[2][4];
+                load_c_frags(C, c, wm);
+                cp_async_wait_all();
+                __syncthreads();
+                update_tile(C, c, Xs, Ys, wm);
+                cta_publish_async(A.f.upd() + cur.s_ij, useq + 1);
+            }
+            if (A.trace) st_p += clock64() - t0, ++n_p;
+        }
+        have = ready, set ^= 1;
+        if (!pipe) {
+            __syncthreads();
+            if (tid == 0) claim_task(&slots[(it + 1) % 3], A.f.next_w(), A.p.wtasks, A.p.n_w, 2);
+            __syncthreads();
+        }
+    }
+    if (A.trace && tid == 0) {
         unsigned long long *st = reinterpret_cast<unsigned long long *>(A.trace) + 4096;
         atomicAdd(st + 0, (unsigned long long)st_wait), atomicAdd(st + 1, (unsigned long long)st_p);
         atomicAdd(st + 2, (unsigned long long)st_u), atomicAdd(st + 3, (unsigned long long)n_p);
         atomicAdd(st + 4, (unsigned long long)n_u), atomicAdd(st + 5, (unsigned long long)(clock64() - t_begin));
         atomicAdd(st + 6, 1ull);
     }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_tile_cholesky(CholArgs A) {
+    if ((int)blockIdx.x < A.p.n_chain_f)
+        run_chain(A);
+    else
+        run_workers(A);
 }
 
 // ---- back-substitution -------------------------------------------------------------------------
@@ -985,6 +1061,7 @@ int ba_launch_tile_cholesky_solve(const CholPlanDev &plan, CholWorkspace &ws, do
     A.trace = trace;
     // CTAs beyond the number of tasks would only poll a counter once
     const int grid_f = std::max(1, std::min(grid, plan.n_chain_f + plan.n_w));
+    A.pipeline = plan.n_w >= 32 * std::max(1, grid_f - plan.n_chain_f);
     const int grid_b = std::max(1, std::min(grid, plan.n_chain_b + plan.n_wb));
     void *args[] = {&A};
     XRB_CUDA(cudaLaunchCooperativeKernel((void *)k_tile_cholesky, dim3(grid_f), dim3(kThreads), args, kSmemBytes, st));
