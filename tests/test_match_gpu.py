@@ -263,3 +263,17 @@ def test_images_above_the_fused_limit_fall_back_to_the_global_state_path():
     off, mm = m.match_pairs(np.array([[0, 1], [2, 0]], dtype=np.int32))
     np.testing.assert_array_equal(mm[off[0]: off[1]], exp)
     np.testing.assert_array_equal(mm[off[1]: off[2]], ol.match_pair(imgs[1][:100], d1))
+
+
+def test_out_of_range_pair_index_is_an_empty_pair(matcher):
+    """An index outside the resident set must not read out of bounds: the pair yields no matches."""
+    imgs, _ = synth.make_images(3, 300, seed=5)
+    matcher.upload_images(imgs)
+    off, mm = matcher.match_pairs(np.array([[0, 1], [0, 7], [-1, 2], [1, 2]], dtype=np.int32), capacity=4 * 300)
+    assert off[2] - off[1] == 0 and off[3] - off[2] == 0
+    for p, (a, b) in ((0, (0, 1)), (3, (1, 2))):
+        e = ol.match_pair(imgs[a], imgs[b])
+        assert np.array_equal(mm[off[p]: off[p + 1]], e)
+    # the default capacity follows the resident image sizes
+    off2, mm2 = matcher.match_pairs(np.array([[0, 1], [1, 2]], dtype=np.int32))
+    assert off2[-1] == (off[1] - off[0]) + (off[4] - off[3])

@@ -436,7 +436,7 @@ int xrb_match_pairs_device(xrb_matcher *m, int n_pairs, const int32_t (*pairs_de
     for (int p0 = 0; p0 < n_pairs; p0 += m->chunk_pairs) {
         const int n = std::min(m->chunk_pairs, n_pairs - p0);
         PairDesc *pd = m->pairdesc.as<PairDesc>();
-        if ((rc = launch_build_pairs(pairs_dev + p0, n, m->offsets_dev.as<int64_t>(), m->block,
+        if ((rc = launch_build_pairs(pairs_dev + p0, n, m->n_images, m->offsets_dev.as<int64_t>(), m->block,
                                      m->max_features, pd, st)))
             return rc;
         if (use_fused(m, max_feat)) {
@@ -527,7 +527,7 @@ int xrb_match_pairs(xrb_matcher *m, int n_pairs, const int32_t (*pairs)[2], floa
         if (c >= 2) XRB_CUDA(cudaStreamWaitEvent(st, m->ev_copied[b], 0));  // packed[b] is free again
         XRB_CUDA(cudaMemcpyAsync(m->pair_idx.p, pairs + p0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
         PairDesc *pd = m->pairdesc.as<PairDesc>();
-        if ((rc = launch_build_pairs(m->pair_idx.as<int32_t[2]>(), n, m->offsets_dev.as<int64_t>(), m->block,
+        if ((rc = launch_build_pairs(m->pair_idx.as<int32_t[2]>(), n, m->n_images, m->offsets_dev.as<int64_t>(), m->block,
                                      m->max_features, pd, st)))
             return rc;
         if (use_fused(m, max_feat)) {

@@ -268,7 +268,7 @@ int launch_finalize(const PairDesc *pairs_dev, int n_pairs, int state_stride, To
 // ---------------------------------------------------------------------------
 // PairDesc table from an index list (device-resident API).
 // ---------------------------------------------------------------------------
-__global__ void build_pairs_kernel(const int32_t (*__restrict__ idx)[2], int n_pairs,
+__global__ void build_pairs_kernel(const int32_t (*__restrict__ idx)[2], int n_pairs, int n_images,
                                    const int64_t *__restrict__ row_offsets,
                                    const uint8_t *__restrict__ block, int max_features,
                                    PairDesc *__restrict__ out) {
@@ -276,6 +276,12 @@ __global__ void build_pairs_kernel(const int32_t (*__restrict__ idx)[2], int n_p
     if (p >= n_pairs) return;
     int a = idx[p][0], b = idx[p][1];
     PairDesc pd;
+    if ((unsigned)a >= (unsigned)n_images || (unsigned)b >= (unsigned)n_images) {
+        // an index outside the resident set: an empty pair (0 matches), never an out-of-bounds read
+        pd.a = pd.b = block, pd.n1 = pd.n2 = 0;
+        out[p] = pd;
+        return;
+    }
     pd.a = block + row_offsets[a] * kDim;
     pd.b = block + row_offsets[b] * kDim;
     int n1 = (int)(row_offsets[a + 1] - row_offsets[a]);
@@ -285,12 +291,12 @@ __global__ void build_pairs_kernel(const int32_t (*__restrict__ idx)[2], int n_p
     out[p] = pd;
 }
 
-int launch_build_pairs(const int32_t (*pairs_idx_dev)[2], int n_pairs,
+int launch_build_pairs(const int32_t (*pairs_idx_dev)[2], int n_pairs, int n_images,
                        const int64_t *row_offsets_dev, const uint8_t *block_dev,
                        int max_features, PairDesc *out_dev, cudaStream_t st) {
     if (n_pairs <= 0) return XRB_OK;
     build_pairs_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(
-        pairs_idx_dev, n_pairs, row_offsets_dev, block_dev, max_features, out_dev);
+        pairs_idx_dev, n_pairs, n_images, row_offsets_dev, block_dev, max_features, out_dev);
     XRB_LAUNCHED();
     XRB_CUDA(cudaGetLastError());
     return XRB_OK;

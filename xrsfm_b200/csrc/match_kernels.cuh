@@ -76,7 +76,7 @@ int launch_finalize(const PairDesc *pairs_dev, int n_pairs, int state_stride, To
                     int32_t *counts_dev, uint32_t (*out_dev)[2], int out_stride,
                     cudaStream_t st);
 
-int launch_build_pairs(const int32_t (*pairs_idx_dev)[2], int n_pairs,
+int launch_build_pairs(const int32_t (*pairs_idx_dev)[2], int n_pairs, int n_images,
                        const int64_t *row_offsets_dev, const uint8_t *block_dev,
                        int max_features, PairDesc *out_dev, cudaStream_t st);
 

@@ -108,6 +108,7 @@ class SiftMatchGPU:
         ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
         rc = _lib.lib().xrb_match_upload_images(self._h, len(arrs), counts.ctypes.data, ptrs)
         _lib.check(rc, "xrb_match_upload_images")
+        self._counts = np.minimum(counts.astype(np.int64), self.GetMaxSift())
 
     def upload_packed(self, row_offsets, block):
         self._ensure()
@@ -116,11 +117,13 @@ class SiftMatchGPU:
         rc = _lib.lib().xrb_match_upload_packed(self._h, len(off) - 1, off.ctypes.data,
                                                 blk.ctypes.data)
         _lib.check(rc, "xrb_match_upload_packed")
+        self._counts = np.minimum(np.diff(off), self.GetMaxSift())
 
     def upload_ftr(self, file_name):
         """Descriptors of the reference's ftr.bin (io_feature.hpp:76-100) straight to HBM."""
         self._ensure()
         _lib.check(_lib.lib().xrb_match_upload_ftr(self._h, str(file_name).encode()), "xrb_match_upload_ftr")
+        self._counts = None  # sizes live in the file: fall back to the allocation's worst case
 
     def match_pairs(self, pairs, distmax=DISTANCE_TH, ratiomax=MAX_RATIO, mutual_best_match=1,
                     max_match=MAX_MATCH, capacity=None):
@@ -130,7 +133,13 @@ class SiftMatchGPU:
         n = pr.shape[0]
         off = np.zeros(n + 1, dtype=np.int64)
         if capacity is None:
-            capacity = n * min(max_match, self.GetMaxSift())
+            # at most min(n1, n2, max_match) matches per pair: bound by the resident image sizes when they are
+            # known (upload_images / upload_packed), not by the worst case of the allocation
+            counts = getattr(self, "_counts", None)
+            if counts is not None and n and pr.min() >= 0 and pr.max() < len(counts):
+                capacity = int(np.minimum(np.minimum(counts[pr[:, 0]], counts[pr[:, 1]]), max_match).sum())
+            else:
+                capacity = n * min(max_match, self.GetMaxSift())
         out = np.zeros((max(capacity, 1), 2), dtype=np.uint32)
         rc = _lib.lib().xrb_match_pairs(self._h, n, pr.ctypes.data, distmax, ratiomax,
                                         int(mutual_best_match), int(max_match), off.ctypes.data,
