@@ -265,15 +265,26 @@ def test_images_above_the_fused_limit_fall_back_to_the_global_state_path():
     np.testing.assert_array_equal(mm[off[1]: off[2]], ol.match_pair(imgs[1][:100], d1))
 
 
-def test_out_of_range_pair_index_is_an_empty_pair(matcher):
-    """An index outside the resident set must not read out of bounds: the pair yields no matches."""
+def test_out_of_range_pair_index(matcher):
+    """Host path: a pair outside the resident set is rejected loudly.  Device path (indices already in HBM, the
+    host cannot look at them): the pair is empty — no out-of-bounds read."""
+    import torch
+    from xrsfm_b200 import _lib
     imgs, _ = synth.make_images(3, 300, seed=5)
     matcher.upload_images(imgs)
-    off, mm = matcher.match_pairs(np.array([[0, 1], [0, 7], [-1, 2], [1, 2]], dtype=np.int32), capacity=4 * 300)
-    assert off[2] - off[1] == 0 and off[3] - off[2] == 0
+    with pytest.raises(_lib.XrbError, match="outside"):
+        matcher.match_pairs(np.array([[0, 1], [0, 7]], dtype=np.int32))
+    pairs = torch.tensor([[0, 1], [0, 7], [-1, 2], [1, 2]], dtype=torch.int32, device="cuda")
+    counts = torch.zeros(4, dtype=torch.int32, device="cuda")
+    out = torch.zeros((4, 300, 2), dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().xrb_match_pairs_device(matcher._h, 4, pairs.data_ptr(), 0.7, 0.8, 1, 16384, counts.data_ptr(),
+                                                 out.data_ptr(), 300, None), "pairs_device")
+    torch.cuda.synchronize()
+    n = counts.cpu().numpy()
+    assert n[1] == 0 and n[2] == 0
     for p, (a, b) in ((0, (0, 1)), (3, (1, 2))):
         e = ol.match_pair(imgs[a], imgs[b])
-        assert np.array_equal(mm[off[p]: off[p + 1]], e)
-    # the default capacity follows the resident image sizes
+        assert np.array_equal(out[p, : n[p]].cpu().numpy().astype(np.uint32), e)
+    # the default capacity of the host path follows the resident image sizes
     off2, mm2 = matcher.match_pairs(np.array([[0, 1], [1, 2]], dtype=np.int32))
-    assert off2[-1] == (off[1] - off[0]) + (off[4] - off[3])
+    assert off2[-1] == n[0] + n[3]
