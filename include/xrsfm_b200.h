@@ -332,8 +332,13 @@ int xrb_debug_column_order(int n_cams, const int32_t *widths, int bw, int allow_
 
 /* Finer split of the last run, out[n >= 8]: [0..2] total ms of k_lin (+ memsets), k_gather,
  * k_cam_blocks; [3] linear solves executed; [4] off-diagonal 6x6 blocks of the reduced camera
- * system; [5] (block, point) incidences the gather walks; [6] reduced system dimension;
- * [7] its half bandwidth. */
+ * system; [5] (block, point) incidences the gather walks; [6] reduced system dimension (variable camera
+ * columns, without padding); [7] its half bandwidth in the natural column order.
+ * n >= 16 adds the plan of the sparse tile Cholesky: [8] independent interiors of the column order (1 =
+ * natural), [9] tile columns, [10] tiles incl. fill, [11] original tiles, [12] flops executed per solve,
+ * [13] / [14] longest dependency paths (tasks) of factorisation / back-substitution, [15] chain CTAs.
+ * n >= 20: [16] CTAs of the fused windowed Schur kernel (0 = gather path), [17] its camera stride,
+ * [18] largest camera span of a point, [19] longest track. */
 int xrb_ba_profile_detail(const xrb_ba_solver *s, double *out, int n);
 
 /* ------------------------------------------------------------------ */

@@ -498,48 +498,21 @@ int do_run(xrb_ba_solver *s, const xrb_ba_options *O, xrb_ba_summary *sum, cudaS
         return XRB_OK;
     }
     if ((rc = reduce_scalar_cost(s, k, s->cur, 0, st, x_cost))) return rc;
-    // ---- Jacobi scaling from the iteration-0 Jacobian
+    // ---- Jacobi scaling from the iteration-0 Jacobian, and ||x|| over the variable blocks of the start point
+    // (both on the device: the scales start at 1, the norm is one reduction; nothing is copied back but a double)
+    double xnorm;
     {
         const BALinSys L = s->linsys();
-        const size_t npl = 3 * (size_t)s->P_local;
-        std::vector<double> ones(std::max<size_t>(npl, (size_t)s->nc), 1.0);
-        if (npl) XRB_CUDA(cudaMemcpyAsync(L.sp, ones.data(), npl * 8, cudaMemcpyHostToDevice, st));
-        if (s->nc) XRB_CUDA(cudaMemcpyAsync(L.sc, ones.data(), (size_t)s->nc * 8, cudaMemcpyHostToDevice, st));
-        XRB_CUDA(cudaMemsetAsync(L.n2c, 0, std::max<size_t>(1, s->nc) * 8, st));
-        XRB_CUDA(cudaStreamSynchronize(st));  // `ones` is pageable
+        XRB_CUDA(cudaMemsetAsync(s->d_scal.p, 0, 2 * SC_COUNT * 8, st));
+        if ((rc = ba_launch_start_norm(s->prob(), s->state(s->cur), L, s->rank == 0, s->scal2() + SC_XNORM2, st))) return rc;
         if ((rc = ba_launch_colnorm(s->prob(), s->state(s->cur), k, L, st))) return rc;
         if ((rc = s->exchange(L.n2c, (size_t)s->nc, st))) return rc;
         if ((rc = ba_launch_finish_scaling(s->prob(), L, st))) return rc;
-        s->launches[0] += 2;
-    }
-    // ||x|| over the variable blocks of the start point
-    double xnorm;
-    {
-        std::vector<double> hq(4 * (size_t)s->C), ht(3 * (size_t)s->C), hX(3 * (size_t)s->P_local);
-        std::vector<int32_t> colq(s->C), colt(s->C);
-        std::vector<uint8_t> pv(s->P_local);
-        XRB_CUDA(cudaMemcpyAsync(hq.data(), s->d_q[s->cur].p, hq.size() * 8, cudaMemcpyDeviceToHost, st));
-        XRB_CUDA(cudaMemcpyAsync(ht.data(), s->d_t[s->cur].p, ht.size() * 8, cudaMemcpyDeviceToHost, st));
-        if (s->P_local) XRB_CUDA(cudaMemcpyAsync(hX.data(), s->d_X[s->cur].p, hX.size() * 8, cudaMemcpyDeviceToHost, st));
-        XRB_CUDA(cudaMemcpyAsync(colq.data(), s->d_colq.p, colq.size() * 4, cudaMemcpyDeviceToHost, st));
-        XRB_CUDA(cudaMemcpyAsync(colt.data(), s->d_colt.p, colt.size() * 4, cudaMemcpyDeviceToHost, st));
-        if (s->P_local) XRB_CUDA(cudaMemcpyAsync(pv.data(), s->d_pt_var.p, pv.size(), cudaMemcpyDeviceToHost, st));
-        XRB_CUDA(cudaStreamSynchronize(st));
+        s->launches[0] += 3;
+        if ((rc = s->exchange(s->scal2(), SC_COUNT, st))) return rc;
         double n2 = 0.0;
-        if (s->rank == 0)
-            for (int c = 0; c < s->C; ++c) {
-                if (colq[c] >= 0) for (int j = 0; j < 4; ++j) n2 += hq[4 * c + j] * hq[4 * c + j];
-                if (colt[c] >= 0) for (int j = 0; j < 3; ++j) n2 += ht[3 * c + j] * ht[3 * c + j];
-            }
-        for (int p = 0; p < s->P_local; ++p)
-            if (pv[p]) for (int j = 0; j < 3; ++j) n2 += hX[3 * (size_t)p + j] * hX[3 * (size_t)p + j];
-        if (s->world > 1) {
-            XRB_CUDA(cudaMemsetAsync(s->d_scal.p, 0, 2 * SC_COUNT * 8, st));
-            XRB_CUDA(cudaMemcpyAsync(s->scal2() + SC_XNORM2, &n2, 8, cudaMemcpyHostToDevice, st));
-            if ((rc = s->exchange(s->scal2(), SC_COUNT, st))) return rc;
-            XRB_CUDA(cudaMemcpyAsync(&n2, s->scal2() + SC_XNORM2, 8, cudaMemcpyDeviceToHost, st));
-            XRB_CUDA(cudaStreamSynchronize(st));
-        }
+        XRB_CUDA(cudaMemcpyAsync(&n2, s->scal2() + SC_XNORM2, 8, cudaMemcpyDeviceToHost, st));
+        XRB_CUDA(cudaStreamSynchronize(st));
         xnorm = std::sqrt(n2);
     }
 

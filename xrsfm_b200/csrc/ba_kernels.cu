@@ -634,6 +634,42 @@ int ba_launch_cam_diag(const BAProblemDev &P, const BAStateDev &x, const BALinSy
     return XRB_OK;
 }
 
+// ||x||^2 over the variable parameter blocks of the start point (what the parameter-tolerance test of the LM
+// loop needs) and the unit Jacobi scales of iteration 0, on the device: one CTA, fixed summation order.
+__global__ void __launch_bounds__(1024)
+k_start_norm(BAProblemDev P, BAStateDev x, BALinSys L, int with_cams, double *__restrict__ out) {
+    double s = 0.0;
+    if (with_cams)
+        for (int c = threadIdx.x; c < P.n_cams; c += 1024) {
+            if (P.colq[c] >= 0)
+                for (int j = 0; j < 4; ++j) s += x.q[4 * (size_t)c + j] * x.q[4 * (size_t)c + j];
+            if (P.colt[c] >= 0)
+                for (int j = 0; j < 3; ++j) s += x.t[3 * (size_t)c + j] * x.t[3 * (size_t)c + j];
+        }
+    for (int p = threadIdx.x; p < P.n_pts_local; p += 1024)
+        if (P.pt_var[p])
+            for (int j = 0; j < 3; ++j) s += x.X[3 * (size_t)p + j] * x.X[3 * (size_t)p + j];
+    for (int i = threadIdx.x; i < 3 * P.n_pts_local; i += 1024) L.sp[i] = 1.0;
+    for (int i = threadIdx.x; i < P.nc; i += 1024) L.sc[i] = 1.0, L.n2c[i] = 0.0;
+    __shared__ double red[32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += red[w];
+        *out = t;
+    }
+}
+
+int ba_launch_start_norm(const BAProblemDev &P, const BAStateDev &x, const BALinSys &L, int with_cams, double *out,
+                         cudaStream_t st) {
+    k_start_norm<<<1, 1024, 0, st>>>(P, x, L, with_cams, out);
+    XRB_LAUNCHED();
+    XRB_CUDA(cudaGetLastError());
+    return XRB_OK;
+}
+
 __global__ void k_set_holes(BALinSys L, const int32_t *__restrict__ holes, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) L.S[L.tm.at(holes[i], holes[i])] = 1.0;

@@ -97,6 +97,9 @@ enum {
 
 int ba_launch_colnorm(const BAProblemDev &P, const BAStateDev &x, const BAConsts &k,
                       const BALinSys &L, cudaStream_t st);
+// unit Jacobi scales + zeroed column norms for iteration 0, and ||x||^2 over the variable blocks -> *out
+int ba_launch_start_norm(const BAProblemDev &P, const BAStateDev &x, const BALinSys &L, int with_cams, double *out,
+                         cudaStream_t st);
 int ba_launch_finish_scaling(const BAProblemDev &P, const BALinSys &L, cudaStream_t st);
 // generation 2: linearise (per-observation records, no atomics) -> gather per block ->
 // camera-major diagonal blocks / gradient / rhs
