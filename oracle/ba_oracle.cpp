@@ -903,7 +903,7 @@ double xro_ba_cost(const xrb_ba_problem *P, const xrb_ba_options *opt) {
     }
     return total;
 }
-/* Post-BA filtering (groundwork: no product kernel yet) — restatement of
+/* Post-BA filtering (the checker of xrsfm_b200/csrc/ba_filter.cu) — restatement of
  * Point3dProcessor::FilterPoints3d / FilterPoint3d / UpdateTrackAngle
  * (src/geometry/track_processor.cc:253-349; Reprojection_Error :19-26; CalculateTriangulationAngle
  * src/geometry/colmap/base/triangulation.cc:124-147; Pose::center src/base/types.h:45) over the

@@ -2,7 +2,7 @@
  * oracle/fmatrix_oracle.cpp — CPU restatement of XRSfM's geometric verification of a matched
  * image pair: LO-RANSAC fundamental matrix (the step that follows path M).
  *
- * TEST INFRASTRUCTURE ONLY (groundwork for the next row: no product code implements this yet).
+ * TEST INFRASTRUCTURE ONLY: the checker of xrsfm_b200/csrc/fm_ransac.cu (tests/test_fm_gpu.py).
  * Nothing under xrsfm_b200/ may link, import or execute this file.
  *
  * PARITY STATUS: "parity unpinned".  The reference ships no tests or golden vectors for this

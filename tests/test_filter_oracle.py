@@ -1,5 +1,5 @@
-"""Post-BA filtering restatement (oracle/ba_oracle.cpp: xro_filter_points3d, groundwork for
-SURVEY.md §8f row 4) against a plain numpy reading of track_processor.cc:253-349.  CPU only."""
+"""Post-BA filtering restatement (oracle/ba_oracle.cpp: xro_filter_points3d, the checker of
+xrb_ba_filter_points3d) against a plain numpy reading of track_processor.cc:253-349.  CPU only."""
 import ctypes as C
 
 import numpy as np

@@ -1,4 +1,4 @@
-"""F-matrix LO-RANSAC oracle (oracle/fmatrix_oracle.cpp; SURVEY.md §8f row 1, groundwork): KATs
+"""F-matrix LO-RANSAC oracle (oracle/fmatrix_oracle.cpp; SURVEY.md §8f row 1, the checker of fm_ransac.cu): KATs
 against numpy (SVD, roots, Sampson error) and synthetic two-view geometry.  CPU only."""
 import ctypes as C
 
