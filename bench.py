@@ -419,6 +419,48 @@ def lba_latency(local_rank, n_windows=40):
                         "call": "xrb_ba_solve_batch (same windows, 8 engines on one device)"}}
 
 
+def pose_refine_rate(local_rank, n_poses=4096, with_cpu=True):
+    """Pose refinement after PnP (pnp.cc:38-71: ten-iteration Ceres solve per registered frame) as ONE launch over
+    n_poses frames through xrb_pose_refine_batch with host buffers (copies inside the timed region), beside the
+    same problems through the BA engine one by one (xrb_ba_solve) and the CPU oracle on a bounded sample."""
+    from xrsfm_b200 import ba, pnp, synth
+    batch = synth.make_pose_batch(n_poses, seed=99, max_pts=300)
+    args = (batch["offsets"], batch["uv"], batch["xyz"], batch["intr"], batch["intr_model"])
+    pnp.refine_poses(*args, batch["q"].copy(), batch["t"].copy(), inlier_mask=batch["inlier"], device=local_rank)
+    best = None
+    for _ in range(3):
+        q, t = batch["q"].copy(), batch["t"].copy()
+        t0 = time.perf_counter()
+        sums = pnp.refine_poses(*args, q, t, inlier_mask=batch["inlier"], device=local_rank)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    its = sum(s["num_lm_iterations"] for s in sums)
+    out = {"poses_per_s": n_poses / best, "ms_per_batch": best * 1e3, "poses": n_poses,
+           "correspondences": int(batch["offsets"][-1]), "lm_iterations_per_pose": its / n_poses,
+           "converged": sum(s["termination_type"] == 0 for s in sums), "gpu_launches": 1,
+           "call": "xrb_pose_refine_batch (one launch, host buffers)"}
+    solver = ba.BASolver(device=local_rank)
+    opts = dict(max_iterations=10, function_tolerance=1e-6, parameter_tolerance=1e-8)
+    scenes = [synth.pose_as_scene(batch, p) for p in range(24)]
+    for sc in scenes[:4]:
+        solver.solve_scene(sc.copy_state(), **opts)
+    t0 = time.perf_counter()
+    for sc in scenes[4:]:
+        solver.solve_scene(sc, **opts)
+    out["ba_engine_per_solve"] = {"poses_per_s": 20 / (time.perf_counter() - t0), "call": "xrb_ba_solve, one pose at a time"}
+    if with_cpu:
+        from tests import oracle_lib as ol
+        o = ol.ba_options(**opts)
+        sample = [synth.pose_as_scene(batch, p) for p in range(3000)]
+        t0 = time.perf_counter()
+        for sc in sample:
+            ol.ba_solve(sc, o, 1)
+        out["cpu_baseline"] = {"value": len(sample) / (time.perf_counter() - t0), "unit": "poses/s", "cores": 1, "kind": "port",
+                               "sample": "3000 of the same poses through oracle/ba_oracle.cpp (one thread each, as the "
+                                         "mapper calls it)"}
+    return out
+
+
 def strip_private(out):
     for k in [k for k in out if k.startswith("_")]:
         del out[k]
@@ -675,6 +717,7 @@ def main():
                 out.update(parity_check(out["_scene"], out["_cfg"], 3, out["_conv_log"]))
             if world == 1:
                 out["lba_latency"] = lba_latency(local_rank)
+                out["pose_refine"] = pose_refine_rate(local_rank, with_cpu=not args.no_cpu_baseline)
             if c4 is not None:
                 ba_rooflines(c4)
                 keep = ("value", "unit", "ms_per_step", "steps", "n_gpus", "config", "e2e", "kernel_ms_per_solve",

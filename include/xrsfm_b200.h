@@ -262,6 +262,28 @@ int xrb_ba_residuals(xrb_ba_solver *s, double *out_residuals);
 int xrb_ba_solve_batch(int device, int n_problems, const xrb_ba_problem *problems, const xrb_ba_options *opt,
                        xrb_ba_summary *summaries, int n_workers);
 
+/* Batched pose refinement: the Ceres block of RegisterImage (src/geometry/pnp.cc:38-71) for n_poses frames in
+ * ONE kernel launch (one CTA per pose, the whole trust-region loop on the device).  Per pose: the 2D-3D
+ * correspondences [offsets[p], offsets[p+1]) of uv (frame.points[p2d_id], pixels) and xyz (the tracks' world
+ * points, constant), an optional inlier mask (SolvePnP_colmap's inlier_mask, pnp.cc:44-46; NULL = all), the
+ * camera (8 padded parameters + model id 0..4, constant) and the pose q (Eigen coeffs x,y,z,w) / t, refined in
+ * place.  Same cost functor, Huber loss, quaternion parameterisation and minimiser semantics as xrb_ba_run with one
+ * variable camera and constant points; xrb_pose_default_options gives what pnp.cc:56-57 sets (Ceres defaults,
+ * max_num_iterations = 10).  final_cost / initial_cost are 1/2 sum rho like ceres::Solver::Summary (pnp.cc:60-67
+ * prints sqrt(cost / num_residuals)). */
+typedef struct xrb_pose_summary {
+    int32_t num_residuals;
+    int32_t num_lm_iterations; /* linear solves executed */
+    int32_t num_successful_steps, num_unsuccessful_steps; /* iteration 0 counts as successful (Ceres) */
+    int32_t termination_type;  /* XRB_BA_CONVERGENCE / NO_CONVERGENCE / FAILURE */
+    int32_t reserved;
+    double initial_cost, final_cost;
+} xrb_pose_summary;
+void xrb_pose_default_options(xrb_ba_options *opt);
+int xrb_pose_refine_batch(int device, int n_poses, const int64_t *offsets, const double *uv, const double *xyz,
+                          const uint8_t *inlier_mask, const double *intr, const int32_t *intr_model, double *q,
+                          double *t, const xrb_ba_options *opt, xrb_pose_summary *summaries);
+
 /* Post-BA point filter on the solver's CURRENT state (after xrb_ba_run / xrb_ba_solve; single GPU).
  * Replaces Point3dProcessor::FilterPoints3d(map, max_re, deg) (src/geometry/track_processor.cc:321-349,
  * FilterPoint3d :279-319, UpdateTrackAngle :253-277, Reprojection_Error :19-26), which the mapper calls

@@ -2,6 +2,7 @@
 // from a scene file, and the matcher façade + the compiled FeatureMatching over a descriptor file.
 // Results go to a file the Python test compares with the ctypes path and the oracle.
 //   shim_gpu_check ba <scene.bin> <out.bin> gba|kgba|lba     shim_gpu_check match <desc.bin> <out.bin>
+//   shim_gpu_check pose <batch.bin> <out.bin>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -11,6 +12,7 @@
 #include "../../xrsfm_b200/shim/SiftMatchGPU_b200.h"
 #include "../../xrsfm_b200/shim/ba_solver_b200.h"
 #include "../../xrsfm_b200/shim/feature_matching_b200.h"
+#include "../../xrsfm_b200/shim/pnp_b200.h"
 
 template <class T>
 static bool rd(FILE *f, T *p, size_t n = 1) { return fread(p, sizeof(T), n, f) == n; }
@@ -134,9 +136,51 @@ static int run_match(const char *desc, const char *out) {
     return 0;
 }
 
+// Pose refinement from C++: frames with their correspondences as RegisterImage holds them (pnp.cc:24-37).
+static int run_pose(const char *in, const char *out) {
+    FILE *f = fopen(in, "rb");
+    if (!f) return 2;
+    int32_t n = 0;
+    rd(f, &n);
+    std::vector<mock::Frame> frames(n);
+    std::vector<mock::CameraT> cams(n);
+    std::vector<std::vector<std::pair<int, int>>> id_pairs(n);
+    std::vector<std::vector<mock::Vec3>> p3d(n);
+    std::vector<std::vector<char>> masks(n);
+    for (int i = 0; i < n; ++i) {
+        int32_t m = 0, model = 0;
+        double intr[8];
+        rd(f, &m), rd(f, &model), rd(f, intr, 8);
+        cams[i].model_id_ = model, cams[i].params_.assign(intr, intr + 8);
+        rd(f, frames[i].Tcw.q.c.v, 4), rd(f, frames[i].Tcw.t.v, 3);
+        frames[i].points.resize(m), p3d[i].resize(m), masks[i].resize(m);
+        for (int k = 0; k < m; ++k) {
+            uint8_t inl = 0;
+            rd(f, frames[i].points[k].v, 2), rd(f, p3d[i][k].v, 3), rd(f, &inl);
+            masks[i][k] = (char)inl;
+            id_pairs[i].push_back({k, k});
+        }
+    }
+    fclose(f);
+    xrsfm_b200::PoseRefiner<mock::Frame> refiner(0);
+    for (int i = 0; i < n; ++i) refiner.Add(frames[i], cams[i], id_pairs[i], p3d[i], masks[i]);
+    if ((int)refiner.size() != n) return 4;
+    if (refiner.Run(false) != XRB_OK) return 3;
+    FILE *o = fopen(out, "wb");
+    if (!o) return 2;
+    for (int i = 0; i < n; ++i) {
+        wr(o, frames[i].Tcw.q.c.v, 4), wr(o, frames[i].Tcw.t.v, 3);
+        const double c[2] = {refiner.summaries[i].initial_cost, refiner.summaries[i].final_cost};
+        wr(o, c, 2);
+    }
+    fclose(o);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc >= 5 && !strcmp(argv[1], "ba")) return run_ba(argv[2], argv[3], argv[4]);
     if (argc >= 4 && !strcmp(argv[1], "match")) return run_match(argv[2], argv[3]);
+    if (argc >= 4 && !strcmp(argv[1], "pose")) return run_pose(argv[2], argv[3]);
     std::fprintf(stderr, "usage: shim_gpu_check ba <scene> <out> gba|kgba|lba | match <desc> <out>\n");
     return 1;
 }

@@ -183,3 +183,27 @@ def test_cpp_matcher_facade_and_feature_matching_on_gpu(tmp_path):
         assert (got == exp).all()
     rc2, n_verified = (int(v) for v in raw[pos: pos + 2])  # (c) matching + batched GPU LO-RANSAC ran end to end
     assert rc2 == 0 and 0 <= n_verified <= len(kept)
+
+
+@pytest.mark.gpu
+def test_cpp_pose_refiner_on_gpu_equals_ctypes(tmp_path):
+    """xrsfm_b200::PoseRefiner (shim/pnp_b200.h, the replacement for pnp.cc:38-71) over mock frames, from C++."""
+    from xrsfm_b200 import pnp, synth
+    exe = _build_gpu_check(tmp_path)
+    b = synth.make_pose_batch(9, seed=41, max_pts=120)
+    with open(tmp_path / "pose.bin", "wb") as f:
+        f.write(struct.pack("<i", 9))
+        for p in range(9):
+            lo, hi = int(b["offsets"][p]), int(b["offsets"][p + 1])
+            f.write(struct.pack("<2i", hi - lo, int(b["intr_model"][p])))
+            f.write(b["intr"][p].tobytes() + b["q"][p].tobytes() + b["t"][p].tobytes())
+            for k in range(lo, hi):
+                f.write(b["uv"][k].tobytes() + b["xyz"][k].tobytes() + struct.pack("<B", int(b["inlier"][k])))
+    subprocess.check_call([exe, "pose", str(tmp_path / "pose.bin"), str(tmp_path / "out.bin")])
+    got = np.fromfile(tmp_path / "out.bin", dtype="<f8").reshape(9, 9)
+    q, t = b["q"].copy(), b["t"].copy()
+    sums = pnp.refine_poses(b["offsets"], b["uv"], b["xyz"], b["intr"], b["intr_model"], q, t, inlier_mask=b["inlier"])
+    assert np.array_equal(got[:, :4], q) and np.array_equal(got[:, 4:7], t)
+    assert np.array_equal(got[:, 7], [s["initial_cost"] for s in sums])
+    assert np.array_equal(got[:, 8], [s["final_cost"] for s in sums])
+    assert np.abs(q - b["q"]).max() > 0

@@ -58,6 +58,13 @@ class BASummary(C.Structure):
     ]
 
 
+class PoseSummary(C.Structure):
+    _fields_ = [("num_residuals", C.c_int32), ("num_lm_iterations", C.c_int32),
+                ("num_successful_steps", C.c_int32), ("num_unsuccessful_steps", C.c_int32),
+                ("termination_type", C.c_int32), ("reserved", C.c_int32),
+                ("initial_cost", C.c_double), ("final_cost", C.c_double)]
+
+
 class ColmapSizes(C.Structure):
     _fields_ = [("n_cameras", C.c_int32), ("n_frames", C.c_int32), ("n_points", C.c_int32),
                 ("n_p2d", C.c_int64), ("n_obs", C.c_int64)]
@@ -100,6 +107,9 @@ SIGNATURES = {
     "xrb_ba_fetch": (C.c_int, [C.c_void_p, C.POINTER(BAProblem)]),
     "xrb_ba_residuals": (C.c_int, [C.c_void_p, C.c_void_p]),
     "xrb_ba_solve_batch": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(BAOptions), C.c_void_p, C.c_int]),
+    "xrb_pose_default_options": (None, [C.POINTER(BAOptions)]),
+    "xrb_pose_refine_batch": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BAOptions), C.c_void_p]),
     "xrb_ba_filter_points3d": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "xrb_ba_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

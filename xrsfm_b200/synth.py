@@ -388,3 +388,117 @@ def make_scene(name, scale=1.0):
     """BASELINE.json configs by name; `scale` shrinks cameras/points for tests."""
     fn, c, p, k, si = SCENES[name]
     return fn(max(4, int(round(c * scale))), max(16, int(round(p * scale))), k, SEED_BASE + si)
+
+
+# ------------------------------------------------------------------------------------------
+# Pose-refinement batches (src/geometry/pnp.cc:38-71): per frame, 2D-3D inlier correspondences
+# and a pose as the P3P LORANSAC leaves it (close to the truth, not at the optimum).
+# ------------------------------------------------------------------------------------------
+POSE_INTRINSICS = {  # model id -> 8 padded parameters (camera_model.hpp:93-210)
+    0: [718.856, 607.19, 185.22, 0, 0, 0, 0, 0],
+    1: [718.856, 712.3, 607.19, 185.22, 0, 0, 0, 0],
+    2: [718.856, 607.19, 185.22, -0.02, 0, 0, 0, 0],
+    3: [718.856, 712.3, 607.19, 185.22, -0.02, 0, 0, 0],
+    4: [718.856, 712.3, 607.19, 185.22, -0.03, 0.01, 1e-3, -5e-4],
+}
+
+
+def project_model(model, intr, x, y):
+    """WorldToImage of camera_model.hpp:93-210 on arrays (ids 0/1 keep the reference's 2 f x + c)."""
+    if model == 0:
+        return intr[0] * 2 * x + intr[1], intr[0] * 2 * y + intr[2]
+    if model == 1:
+        return intr[0] * 2 * x + intr[2], intr[1] * 2 * y + intr[3]
+    r2 = x * x + y * y
+    if model == 2:
+        return intr[0] * (x + x * intr[3] * r2) + intr[1], intr[0] * (y + y * intr[3] * r2) + intr[2]
+    if model == 3:
+        return intr[0] * (x + x * intr[4] * r2) + intr[2], intr[1] * (y + y * intr[4] * r2) + intr[3]
+    k1, k2, p1, p2 = intr[4:8]
+    rad = k1 * r2 + k2 * r2 * r2
+    du = x * rad + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+    dv = y * rad + 2 * p2 * x * y + p1 * (r2 + 2 * y * y)
+    return intr[0] * (x + du) + intr[2], intr[1] * (y + dv) + intr[3]
+
+
+def make_pose_batch(n_poses, seed, min_pts=20, max_pts=400, noise_px=0.7, outlier_frac=0.05, rot_deg=1.0,
+                    trans_frac=0.02, models=(2, 4, 3, 1, 0), with_mask=True, behind_frac=0.0):
+    """-> dict(offsets, uv, xyz, inlier, intr, intr_model, q, t, gt_q, gt_t): n_poses independent frames.
+
+    Each frame sees between min_pts and max_pts points 4..40 units in front of it; its starting pose is the truth
+    rotated by ~rot_deg and shifted by ~trans_frac of the mean depth; a fraction of the measurements are gross
+    outliers (the Huber loss has work to do) and, with `with_mask`, a few correspondences are masked out the way
+    SolvePnP_colmap's inlier_mask would.  `behind_frac` puts some points behind the camera (the constant-residual
+    branch of the cost functor)."""
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(min_pts, max_pts + 1, size=n_poses)
+    offsets = np.zeros(n_poses + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    total = int(offsets[-1])
+    uv = np.empty((total, 2))
+    xyz = np.empty((total, 3))
+    inlier = np.ones(total, dtype=np.uint8)
+    intr = np.zeros((n_poses, 8))
+    intr_model = np.zeros(n_poses, dtype=np.int32)
+    q = np.empty((n_poses, 4))
+    t = np.empty((n_poses, 3))
+    gt_q = np.empty((n_poses, 4))
+    gt_t = np.empty((n_poses, 3))
+    for p in range(n_poses):
+        lo, hi = int(offsets[p]), int(offsets[p + 1])
+        n = hi - lo
+        model = models[p % len(models)]
+        intr_model[p] = model
+        intr[p] = POSE_INTRINSICS[model]
+        centre = rng.normal(0.0, 20.0, size=3)
+        target = centre + rng.normal(0.0, 1.0, size=3)
+        qg, tg = look_at_pose(centre, target)
+        R = rotmat_from_quat(qg)
+        depth = rng.uniform(4.0, 40.0, size=n)
+        xn = rng.uniform(-0.7, 0.7, size=n)
+        yn = rng.uniform(-0.22, 0.22, size=n)
+        pc = np.stack([xn * depth, yn * depth, depth], axis=1)
+        X = (pc - tg) @ R  # Rcw^T (pc - t)
+        u, v = project_model(model, intr[p], xn, yn)
+        m = np.stack([u, v], axis=1) + rng.normal(0.0, noise_px, size=(n, 2))
+        n_out = int(round(outlier_frac * n))
+        if n_out:
+            oi = rng.choice(n, size=n_out, replace=False)
+            ang = rng.uniform(0, 2 * np.pi, size=n_out)
+            mag = rng.uniform(20.0, 100.0, size=n_out)
+            m[oi] += np.stack([mag * np.cos(ang), mag * np.sin(ang)], axis=1)
+        n_behind = int(round(behind_frac * n))
+        if n_behind:
+            bi = rng.choice(n, size=n_behind, replace=False)
+            X[bi] = centre - 0.5 * (X[bi] - centre)
+        if with_mask and n > min_pts:
+            inlier[lo + rng.choice(n, size=max(1, n // 16), replace=False)] = 0
+        uv[lo:hi], xyz[lo:hi] = m, X
+        w = rng.normal(0.0, np.deg2rad(rot_deg), size=3) * 0.5
+        dq = np.array([w[0], w[1], w[2], 1.0])
+        dq /= np.linalg.norm(dq)
+        q0 = quat_mul(dq, qg)
+        q[p] = q0 / np.linalg.norm(q0)
+        t[p] = tg + rng.normal(0.0, trans_frac * depth.mean(), size=3)
+        gt_q[p], gt_t[p] = qg, tg
+    return dict(offsets=offsets, uv=np.ascontiguousarray(uv), xyz=np.ascontiguousarray(xyz), inlier=inlier,
+                intr=intr, intr_model=intr_model, q=np.ascontiguousarray(q), t=np.ascontiguousarray(t),
+                gt_q=gt_q, gt_t=gt_t)
+
+
+def pose_as_scene(batch, p):
+    """Pose p of a make_pose_batch dict as a one-camera BAScene (points constant, masked correspondences dropped):
+    the same problem in xrb_ba_problem form, for xrb_ba_solve and the BA oracle."""
+    lo, hi = int(batch["offsets"][p]), int(batch["offsets"][p + 1])
+    keep = np.flatnonzero(batch["inlier"][lo:hi]) + lo
+    n = keep.shape[0]
+    return BAScene(
+        n_cams=1, n_pts=n, n_obs=n, n_intr=1,
+        cam_q=batch["q"][p:p + 1].copy(), cam_t=batch["t"][p:p + 1].copy(),
+        pts=np.ascontiguousarray(batch["xyz"][keep]),
+        intr=batch["intr"][p:p + 1].copy(), intr_model=batch["intr_model"][p:p + 1].copy(),
+        cam_intr=np.zeros(1, dtype=np.int32),
+        obs_cam=np.zeros(n, dtype=np.int32), obs_pt=np.arange(n, dtype=np.int32),
+        obs_uv=np.ascontiguousarray(batch["uv"][keep]),
+        cam_q_fixed=np.zeros(1, dtype=np.uint8), cam_t_fixed=np.zeros(1, dtype=np.uint8),
+        pt_fixed=np.ones(n, dtype=np.uint8))
