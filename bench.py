@@ -434,10 +434,10 @@ def pose_refine_rate(local_rank, n_poses=4096, with_cpu=True):
         sums = pnp.refine_poses(*args, q, t, inlier_mask=batch["inlier"], device=local_rank)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    its = sum(s["num_lm_iterations"] for s in sums)
-    out = {"poses_per_s": n_poses / best, "ms_per_batch": best * 1e3, "poses": n_poses,
+    its = int(sums["num_lm_iterations"].sum())
+    out = {"poses_per_s": n_poses / best, "ms_per_batch": best * 1e3, "kernel_ms": pnp.last_kernel_ms(local_rank), "poses": n_poses,
            "correspondences": int(batch["offsets"][-1]), "lm_iterations_per_pose": its / n_poses,
-           "converged": sum(s["termination_type"] == 0 for s in sums), "gpu_launches": 1,
+           "converged": int((sums["termination_type"] == 0).sum()), "gpu_launches": 1,
            "call": "xrb_pose_refine_batch (one launch, host buffers)"}
     solver = ba.BASolver(device=local_rank)
     opts = dict(max_iterations=10, function_tolerance=1e-6, parameter_tolerance=1e-8)

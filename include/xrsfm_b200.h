@@ -283,6 +283,8 @@ void xrb_pose_default_options(xrb_ba_options *opt);
 int xrb_pose_refine_batch(int device, int n_poses, const int64_t *offsets, const double *uv, const double *xyz,
                           const uint8_t *inlier_mask, const double *intr, const int32_t *intr_model, double *q,
                           double *t, const xrb_ba_options *opt, xrb_pose_summary *summaries);
+/* Device time (ms, CUDA events) of the kernel of the last xrb_pose_refine_batch on `device`; < 0 if none yet. */
+double xrb_pose_last_kernel_ms(int device);
 
 /* Post-BA point filter on the solver's CURRENT state (after xrb_ba_run / xrb_ba_solve; single GPU).
  * Replaces Point3dProcessor::FilterPoints3d(map, max_re, deg) (src/geometry/track_processor.cc:321-349,

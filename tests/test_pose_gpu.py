@@ -125,8 +125,8 @@ def test_pose_result_does_not_depend_on_the_batch():
 def test_pose_edge_cases():
     from xrsfm_b200 import _lib, pnp
     # no poses at all
-    assert pnp.refine_poses(np.zeros(1, dtype=np.int64), np.zeros((0, 2)), np.zeros((0, 3)), np.zeros((0, 8)),
-                            np.zeros(0, dtype=np.int32), np.zeros((0, 4)), np.zeros((0, 3))) == []
+    assert len(pnp.refine_poses(np.zeros(1, dtype=np.int64), np.zeros((0, 2)), np.zeros((0, 3)), np.zeros((0, 8)),
+                                np.zeros(0, dtype=np.int32), np.zeros((0, 4)), np.zeros((0, 3)))) == 0
     # a pose without correspondences, one whose correspondences are all masked out, and a regular one between them
     b = synth.make_pose_batch(3, seed=16, with_mask=False)
     lo1, hi1 = int(b["offsets"][1]), int(b["offsets"][2])

@@ -204,6 +204,5 @@ def test_cpp_pose_refiner_on_gpu_equals_ctypes(tmp_path):
     q, t = b["q"].copy(), b["t"].copy()
     sums = pnp.refine_poses(b["offsets"], b["uv"], b["xyz"], b["intr"], b["intr_model"], q, t, inlier_mask=b["inlier"])
     assert np.array_equal(got[:, :4], q) and np.array_equal(got[:, 4:7], t)
-    assert np.array_equal(got[:, 7], [s["initial_cost"] for s in sums])
-    assert np.array_equal(got[:, 8], [s["final_cost"] for s in sums])
+    assert np.array_equal(got[:, 7], sums["initial_cost"]) and np.array_equal(got[:, 8], sums["final_cost"])
     assert np.abs(q - b["q"]).max() > 0

@@ -110,6 +110,7 @@ SIGNATURES = {
     "xrb_pose_default_options": (None, [C.POINTER(BAOptions)]),
     "xrb_pose_refine_batch": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BAOptions), C.c_void_p]),
+    "xrb_pose_last_kernel_ms": (C.c_double, [C.c_int]),
     "xrb_ba_filter_points3d": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "xrb_ba_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <mutex>
 
 #include "ba_model.cuh"
 #include "common.cuh"
@@ -316,6 +317,17 @@ k_pose_refine(PoseBatch B, xrb_ba_options O) {
     }
 }
 
+constexpr int kMaxDevices = 64;
+struct PoseWorkspace {  // grow-only device buffers, a stream and two events per device, kept between calls
+    std::mutex mu;
+    DevBuf off, uv, xyz, in, intr, model, q, t, sum;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int sms = 148;
+    double kernel_ms = -1.0;
+};
+PoseWorkspace g_ws[kMaxDevices];
+
 }  // namespace
 }  // namespace xrb
 
@@ -360,46 +372,56 @@ int xrb_pose_refine_batch(int device, int n_poses, const int64_t *offsets, const
     int rc = select_device(device);
     if (rc) return rc;
     static_assert(sizeof(long long) == sizeof(int64_t), "");
-    DevBuf d_off, d_uv, d_xyz, d_in, d_intr, d_model, d_q, d_t, d_sum;
-    const size_t tot = (size_t)std::max<int64_t>(total, 1), np = (size_t)n_poses;
-    if ((rc = d_off.reserve((np + 1) * 8)) || (rc = d_uv.reserve(tot * 16)) || (rc = d_xyz.reserve(tot * 24)) ||
-        (rc = d_in.reserve(tot)) || (rc = d_intr.reserve(np * 64)) || (rc = d_model.reserve(np * 4)) ||
-        (rc = d_q.reserve(np * 32)) || (rc = d_t.reserve(np * 24)) || (rc = d_sum.reserve(np * sizeof(xrb_pose_summary))))
-        return rc;
-    cudaStream_t st;
-    XRB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    XRB_CUDA(cudaMemcpyAsync(d_off.p, offsets, (np + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (total) {
-        XRB_CUDA(cudaMemcpyAsync(d_uv.p, uv, (size_t)total * 16, cudaMemcpyHostToDevice, st));
-        XRB_CUDA(cudaMemcpyAsync(d_xyz.p, xyz, (size_t)total * 24, cudaMemcpyHostToDevice, st));
-        if (inlier_mask) XRB_CUDA(cudaMemcpyAsync(d_in.p, inlier_mask, (size_t)total, cudaMemcpyHostToDevice, st));
+    if (device < 0 || device >= kMaxDevices) {
+        set_error("pose_refine_batch: device %d out of range", device);
+        return XRB_ERR_INVALID;
     }
-    XRB_CUDA(cudaMemcpyAsync(d_intr.p, intr, np * 64, cudaMemcpyHostToDevice, st));
-    XRB_CUDA(cudaMemcpyAsync(d_model.p, intr_model, np * 4, cudaMemcpyHostToDevice, st));
-    XRB_CUDA(cudaMemcpyAsync(d_q.p, q, np * 32, cudaMemcpyHostToDevice, st));
-    XRB_CUDA(cudaMemcpyAsync(d_t.p, t, np * 24, cudaMemcpyHostToDevice, st));
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const int grid = std::min(n_poses, sms * 8);
-    PoseBatch B{n_poses, d_off.as<long long>(), d_uv.as<double>(), d_xyz.as<double>(),
-                inlier_mask ? d_in.as<uint8_t>() : nullptr, d_intr.as<double>(), d_model.as<int32_t>(),
-                d_q.as<double>(), d_t.as<double>(), d_sum.as<xrb_pose_summary>()};
-    // offsets are relative to the arrays as passed
+    PoseWorkspace &W = g_ws[device];
+    std::lock_guard<std::mutex> lock(W.mu);  // one batch at a time per device: the workspace is shared
+    const size_t tot = (size_t)std::max<int64_t>(total, 1), np = (size_t)n_poses;
+    if ((rc = W.off.reserve((np + 1) * 8)) || (rc = W.uv.reserve(tot * 16)) || (rc = W.xyz.reserve(tot * 24)) ||
+        (rc = W.in.reserve(tot)) || (rc = W.intr.reserve(np * 64)) || (rc = W.model.reserve(np * 4)) ||
+        (rc = W.q.reserve(np * 32)) || (rc = W.t.reserve(np * 24)) || (rc = W.sum.reserve(np * sizeof(xrb_pose_summary))))
+        return rc;
+    if (!W.st) {
+        XRB_CUDA(cudaStreamCreateWithFlags(&W.st, cudaStreamNonBlocking));
+        XRB_CUDA(cudaEventCreate(&W.ev[0]));
+        XRB_CUDA(cudaEventCreate(&W.ev[1]));
+        cudaDeviceGetAttribute(&W.sms, cudaDevAttrMultiProcessorCount, device);
+    }
+    cudaStream_t st = W.st;
+    XRB_CUDA(cudaMemcpyAsync(W.off.p, offsets, (np + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (total) {
+        XRB_CUDA(cudaMemcpyAsync(W.uv.p, uv, (size_t)total * 16, cudaMemcpyHostToDevice, st));
+        XRB_CUDA(cudaMemcpyAsync(W.xyz.p, xyz, (size_t)total * 24, cudaMemcpyHostToDevice, st));
+        if (inlier_mask) XRB_CUDA(cudaMemcpyAsync(W.in.p, inlier_mask, (size_t)total, cudaMemcpyHostToDevice, st));
+    }
+    XRB_CUDA(cudaMemcpyAsync(W.intr.p, intr, np * 64, cudaMemcpyHostToDevice, st));
+    XRB_CUDA(cudaMemcpyAsync(W.model.p, intr_model, np * 4, cudaMemcpyHostToDevice, st));
+    XRB_CUDA(cudaMemcpyAsync(W.q.p, q, np * 32, cudaMemcpyHostToDevice, st));
+    XRB_CUDA(cudaMemcpyAsync(W.t.p, t, np * 24, cudaMemcpyHostToDevice, st));
+    const int grid = std::min(n_poses, W.sms * 8);
+    PoseBatch B{n_poses, W.off.as<long long>(), W.uv.as<double>(), W.xyz.as<double>(),
+                inlier_mask ? W.in.as<uint8_t>() : nullptr, W.intr.as<double>(), W.model.as<int32_t>(),
+                W.q.as<double>(), W.t.as<double>(), W.sum.as<xrb_pose_summary>()};
+    XRB_CUDA(cudaEventRecord(W.ev[0], st));
     k_pose_refine<<<grid, kPoseThreads, 0, st>>>(B, *opt);
     XRB_LAUNCHED();
     XRB_CUDA(cudaGetLastError());
-    XRB_CUDA(cudaMemcpyAsync(q, d_q.p, np * 32, cudaMemcpyDeviceToHost, st));
-    XRB_CUDA(cudaMemcpyAsync(t, d_t.p, np * 24, cudaMemcpyDeviceToHost, st));
-    XRB_CUDA(cudaMemcpyAsync(summaries, d_sum.p, np * sizeof(xrb_pose_summary), cudaMemcpyDeviceToHost, st));
-    const cudaError_t e = cudaStreamSynchronize(st);
-    cudaStreamDestroy(st);
-    d_off.release(), d_uv.release(), d_xyz.release(), d_in.release(), d_intr.release(), d_model.release();
-    d_q.release(), d_t.release(), d_sum.release();
-    if (e != cudaSuccess) {
-        set_error("pose_refine_batch: %s", cudaGetErrorString(e));
-        return XRB_ERR_CUDA;
-    }
+    XRB_CUDA(cudaEventRecord(W.ev[1], st));
+    XRB_CUDA(cudaMemcpyAsync(q, W.q.p, np * 32, cudaMemcpyDeviceToHost, st));
+    XRB_CUDA(cudaMemcpyAsync(t, W.t.p, np * 24, cudaMemcpyDeviceToHost, st));
+    XRB_CUDA(cudaMemcpyAsync(summaries, W.sum.p, np * sizeof(xrb_pose_summary), cudaMemcpyDeviceToHost, st));
+    XRB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, W.ev[0], W.ev[1]) == cudaSuccess) W.kernel_ms = ms;
     return XRB_OK;
+}
+
+double xrb_pose_last_kernel_ms(int device) {
+    if (device < 0 || device >= kMaxDevices) return -1.0;
+    std::lock_guard<std::mutex> lock(g_ws[device].mu);
+    return g_ws[device].kernel_ms;
 }
 
 }  // extern "C"

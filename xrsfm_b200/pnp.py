@@ -12,6 +12,12 @@ from . import _lib
 
 TERMINATION = {0: "Convergence", 1: "No convergence", 2: "Failure"}
 
+# xrb_pose_summary, one record per pose
+SUMMARY_DTYPE = np.dtype([("num_residuals", "<i4"), ("num_lm_iterations", "<i4"), ("num_successful_steps", "<i4"),
+                          ("num_unsuccessful_steps", "<i4"), ("termination_type", "<i4"), ("reserved", "<i4"),
+                          ("initial_cost", "<f8"), ("final_cost", "<f8")])
+assert SUMMARY_DTYPE.itemsize == C.sizeof(_lib.PoseSummary)
+
 
 def make_options(**kw):
     """ceres::Solver::Options as pnp.cc:56-57 leaves them (defaults, max_num_iterations = 10) + cost constants."""
@@ -29,7 +35,7 @@ def refine_poses(offsets, uv, xyz, intr, intr_model, q, t, inlier_mask=None, dev
 
     offsets[n+1] (int64) delimit each pose's correspondences in uv[total,2] (pixels) / xyz[total,3] (world);
     intr[n,8] / intr_model[n] are the (constant) cameras; q[n,4] (x,y,z,w) and t[n,3] are updated in place.
-    Returns a list of dicts (one per pose) with the summary fields of ``xrb_pose_summary``."""
+    Returns a structured array (SUMMARY_DTYPE, one ``xrb_pose_summary`` record per pose)."""
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     n = offsets.shape[0] - 1
     uv = np.ascontiguousarray(uv, dtype=np.float64)
@@ -51,8 +57,13 @@ def refine_poses(offsets, uv, xyz, intr, intr_model, q, t, inlier_mask=None, dev
             raise ValueError("inlier_mask must be [total]")
         mask_ptr = inlier_mask.ctypes.data
     o = make_options(**opts)
-    sums = (_lib.PoseSummary * max(n, 1))()
+    sums = np.zeros(n, dtype=SUMMARY_DTYPE)
     _lib.check(_lib.lib().xrb_pose_refine_batch(device, n, offsets.ctypes.data, uv.ctypes.data, xyz.ctypes.data,
                                                 mask_ptr, intr.ctypes.data, intr_model.ctypes.data, q.ctypes.data,
-                                                t.ctypes.data, C.byref(o), sums), "xrb_pose_refine_batch")
-    return [{k: getattr(sums[i], k) for k, _ in _lib.PoseSummary._fields_ if k != "reserved"} for i in range(n)]
+                                                t.ctypes.data, C.byref(o), sums.ctypes.data), "xrb_pose_refine_batch")
+    return sums
+
+
+def last_kernel_ms(device=0):
+    """Device time of the kernel of the last refine_poses call on `device` (CUDA events)."""
+    return _lib.lib().xrb_pose_last_kernel_ms(device)
