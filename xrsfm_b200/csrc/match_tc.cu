@@ -30,7 +30,10 @@ constexpr int kTileN = 256;          // descriptors of image 2 per MMA tile (TME
 constexpr int kAStages = 3;
 constexpr int kATileBytes = kTileM * kDim;    // 16 KB
 constexpr int kBoxRows = 128;                 // TMA box: 128 rows x 128 bytes
-constexpr int kThreads = 32 * 10;
+constexpr int kEpiWarps = 16;        // epilogue warps: 4 per TMEM lane quarter, each owns kTileN / 4 columns of a tile
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kColsPerWarp = kTileN / (kEpiWarps / 4);
+constexpr int kThreads = 32 * (2 + kEpiWarps);
 // Two flavours of the kernel (template parameter kFused):
 //  false: top-2 state in global memory (any image size), resident B group of 1024 descriptors,
 //         thresholds/compaction in finalize_kernel afterwards;
@@ -43,8 +46,8 @@ template <bool kFused> struct Cfg {
     static constexpr int kGroupN = kFused ? 512 : 1024;  // resident B descriptors per group
     static constexpr int kBGroupBytes = kGroupN * kDim;
     static constexpr int kStateBytes = kFused ? 2 * kFusedMax * 8 : 0;
-    static constexpr int kQueueBytes = kFused ? 8 * kLaneQueue * 32 * 8 : 0;
-    static constexpr int kScratchBytes = kFused ? 8 * 16 * 32 * 4 : 0;  // per lane: one group of 16 accumulators
+    static constexpr int kQueueBytes = kFused ? kEpiWarps * kLaneQueue * 32 * 8 : 0;
+    static constexpr int kScratchBytes = kFused ? kEpiWarps * 16 * 32 * 4 : 0;  // per lane: one group of 16 accumulators
     static constexpr int kSmemBytes = kBGroupBytes + kAStages * kATileBytes + kStateBytes + kQueueBytes +
                                       kScratchBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -195,7 +198,7 @@ __device__ __noinline__ void global_slow16(Top2State rows, Top2State cols, size_
     }
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 struct FusedArgs {
     const float *dist_tab;  // float(acos(double(min(v * 2^-18, 1)))) for v = 0 .. 2^18
@@ -243,7 +246,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&bars->t_full[b]), 1);
-            mbar_init(smem_u32(&bars->t_empty[b]), 8);  // one arrival per epilogue warp
+            mbar_init(smem_u32(&bars->t_empty[b]), kEpiWarps);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -319,10 +322,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
     } else {
         // ===================== epilogue =====================
-        const int ew = warp - 2;            // 0..7
-        const int et = threadIdx.x - 64;    // 0..255 among the epilogue threads
+        const int ew = warp - 2;            // 0..kEpiWarps-1
+        const int et = threadIdx.x - 64;    // 0..kEpiThreads-1 among the epilogue threads
         const int quarter = warp & 3;       // TMEM lane quarter this warp may touch (warp id % 4)
-        const int half = ew >> 2;           // which 128-column half of the 256-column tile
+        const int part = ew >> 2;           // which kColsPerWarp-column part of the 256-column tile
         const int vlow = *vlow_ptr;
         // per-lane private candidate queues: q[slot][lane]; no coordination needed to append
         unsigned long long *q = queues + ew * (kLaneQueue * 32) + lane;
@@ -330,7 +333,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         int qn = 0;  // this lane's fill
         uint32_t t_it = 0;
         if (kFused) {
-            for (int z = et; z < 2 * kFusedMax; z += 256) st_rows[z] = 0ull;
+            for (int z = et; z < 2 * kFusedMax; z += kEpiThreads) st_rows[z] = 0ull;
             epi_bar();
         }
         auto drain = [&]() {
@@ -355,18 +358,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         const int tb = t_it & 1;
                         mbar_wait(smem_u32(&bars->t_full[tb]), (t_it >> 1) & 1);
                         tc_fence_after();
-                        const int col_tile = g0 + ns * kTileN + half * 128;
-                        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + tb * kTileN + half * 128;
+                        const int col_tile = g0 + ns * kTileN + part * kColsPerWarp;
+                        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + tb * kTileN + part * kColsPerWarp;
                         // 64 columns (2 x 32x32b.x32) in flight per wait: the register file of an
                         // SM sub-partition (16 K) holds 3 of the CTA's 10 warps, which caps a thread
                         // at 168 registers — 128 accumulators in flight would spill
 #pragma unroll 1
-                        for (int hh = 0; hh < 2; ++hh) {
+                        for (int hh = 0; hh < kColsPerWarp / 64; ++hh) {
                         int v[64];
                         ldtm32(taddr + hh * 64, v);
                         ldtm32(taddr + hh * 64 + 32, v + 32);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (hh == 1) {  // accumulator fully read: hand the TMEM buffer back
+                        if (hh == kColsPerWarp / 64 - 1) {  // accumulator fully read: hand the TMEM buffer back
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(smem_u32(&bars->t_empty[tb]));
@@ -447,7 +450,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 int *wsum = reinterpret_cast<int *>(queues);  // queues are idle now
                 int running = 0;
                 uint32_t(*dst)[2] = fa.out + (size_t)p * fa.out_stride;
-                for (int chunk = 0; chunk < pd.n1; chunk += 256) {
+                for (int chunk = 0; chunk < pd.n1; chunk += kEpiThreads) {
                     const int r = chunk + et;
                     int flag = 0, j = -1;
                     if (r < pd.n1) {
@@ -470,7 +473,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     epi_bar();
                     int before = 0, total = 0;
 #pragma unroll
-                    for (int w = 0; w < 8; ++w) {
+                    for (int w = 0; w < kEpiWarps; ++w) {
                         const int c = wsum[w];
                         before += w < ew ? c : 0;
                         total += c;
@@ -481,8 +484,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     epi_bar();
                 }
                 if (et == 0) fa.counts[p] = running < fa.max_match ? running : fa.max_match;
-                for (int z = et; z < pd.n1; z += 256) st_rows[z] = 0ull;
-                for (int z = et; z < pd.n2; z += 256) st_cols[z] = 0ull;
+                for (int z = et; z < pd.n1; z += kEpiThreads) st_rows[z] = 0ull;
+                for (int z = et; z < pd.n2; z += kEpiThreads) st_cols[z] = 0ull;
                 epi_bar();
             }
         }
