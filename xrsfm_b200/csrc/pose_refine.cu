@@ -198,7 +198,7 @@ __device__ void solve_step(PoseShared &S, double radius) {
     S.step[0] = model, S.step[1] = sqrt(sn2), S.step[2] = sqrt(xn2), S.step[3] = (!bad && finite) ? 1.0 : 0.0;
 }
 
-__global__ void __launch_bounds__(kPoseThreads)
+__global__ void __launch_bounds__(kPoseThreads, 3)
 k_pose_refine(PoseBatch B, xrb_ba_options O) {
     __shared__ PoseShared S;
     const BAConsts k{O.huber_a, O.huber_a * O.huber_a, O.min_depth, O.neg_depth_residual};
