@@ -11,8 +11,11 @@
 //            ring of A tiles (128 descriptors = 16 KB each)
 //   warp 1   TMEM allocator + MMA issuer: per (A tile, 256-column slice of the B group)
 //            4 x tcgen05.mma.cta_group::1.kind::i8 (M128 N256 K32), double-buffered in TMEM
-//   warps 2-9 epilogue: TMEM -> registers (32x32b.x32), VIMNMX3 max-filter against v_low,
-//            rare candidates pushed into the per-row / per-column top-2 state
+//   warps 2-17 epilogue (four per TMEM lane quarter, each owns 64 of a tile's 256 columns): TMEM -> registers
+//            (2 x 32x32b.x32 per wait), VIMNMX3 max-filter against v_low, rare candidates pushed into the
+//            per-row / per-column top-2 state.  Sixteen warps instead of eight put four on every scheduler:
+//            one warp's tcgen05.ld round trip and candidate path overlap with three others (135 k -> 197 k
+//            pairs/s; profiles/r02_match_ncu_summary.md)
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -360,9 +363,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         tc_fence_after();
                         const int col_tile = g0 + ns * kTileN + part * kColsPerWarp;
                         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + tb * kTileN + part * kColsPerWarp;
-                        // 64 columns (2 x 32x32b.x32) in flight per wait: the register file of an
-                        // SM sub-partition (16 K) holds 3 of the CTA's 10 warps, which caps a thread
-                        // at 168 registers — 128 accumulators in flight would spill
+                        // 64 columns (2 x 32x32b.x32) in flight per wait: 18 warps share the SM's 64 K
+                        // registers, which caps a thread at 112 (ptxas settles on 96) — more accumulators
+                        // in flight would spill
 #pragma unroll 1
                         for (int hh = 0; hh < kColsPerWarp / 64; ++hh) {
                         int v[64];
