@@ -716,8 +716,13 @@ def main():
             if not args.no_cpu_baseline:
                 out.update(parity_check(out["_scene"], out["_cfg"], 3, out["_conv_log"]))
             if world == 1:
-                out["lba_latency"] = lba_latency(local_rank)
-                out["pose_refine"] = pose_refine_rate(local_rank, with_cpu=not args.no_cpu_baseline)
+                # secondary objects: a failure here is reported in place, it must not take the headline with it
+                for key, fn in (("lba_latency", lambda: lba_latency(local_rank)),
+                                ("pose_refine", lambda: pose_refine_rate(local_rank, with_cpu=not args.no_cpu_baseline))):
+                    try:
+                        out[key] = fn()
+                    except Exception as e:  # noqa: BLE001
+                        out[key] = {"error": f"{type(e).__name__}: {e}"}
             if c4 is not None:
                 ba_rooflines(c4)
                 keep = ("value", "unit", "ms_per_step", "steps", "n_gpus", "config", "e2e", "kernel_ms_per_solve",
