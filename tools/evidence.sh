@@ -2,8 +2,8 @@
 # One GPU-box call that refreshes the measured evidence under gpurun_out/ (copy what is to be
 # judged into profiles/ afterwards).  Usage:
 #   gpurun --timeout 1200 -- 'bash tools/evidence.sh r02a'
-# Produces  <tag>_bench.json  <tag>_ref.json  <tag>_ba_launches.csv  <tag>_match.ncu-rep
-#           <tag>_ba_kernels.ncu-rep  <tag>_chol_trace.txt
+# Produces  <tag>_bench.json  <tag>_ref.json  <tag>_ba_launches.csv  <tag>_chol_trace.txt and the ncu reports
+#           <tag>_{chol,schur,fm,filter,match,pose}.ncu-rep
 set -u
 TAG=${1:-rXX}
 OUT=gpurun_out
@@ -27,4 +27,9 @@ timeout 200 ncu --set full --clock-control none --import-source on -k regex:"k_f
     python -m pytest tests/test_fm_gpu.py -m gpu -q -k equals > /dev/null 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"k_filter_points" -c 1 -f -o $OUT/${TAG}_filter \
     python -m pytest tests/test_ba_gpu.py -q -k "filter and seq" > /dev/null 2>&1
-ls -la $OUT | tail -14
+# the matcher kernel (148 pairs, one per SM) and the pose-refinement kernel (4 096 poses)
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:score_tc -s 1 -c 1 -f -o $OUT/${TAG}_match \
+    python tools/ncu_match.py 3 > /dev/null 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_pose_refine -s 1 -c 1 -f -o $OUT/${TAG}_pose \
+    python -c "import bench; bench.pose_refine_rate(0, with_cpu=False)" > /dev/null 2>&1
+ls -la $OUT | tail -16
