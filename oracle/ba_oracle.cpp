@@ -22,6 +22,9 @@
  *   constant blocks / gauge           ba_solver.cc:602-621, 655-663, 380-389
  *   solver options                    ba_solver.cc:70-77, 624-634, 665-670
  *   summary fields printed            ba_solver.cc:14-68
+ *   pose refinement after PnP         src/geometry/pnp.cc:38-71 (the same functor, loss and parameterisation with one
+ *                                     variable camera and constant points: xro_ba_solve on that problem is the checker
+ *                                     of xrsfm_b200/csrc/pose_refine.cu, tests/test_pose_gpu.py)
  * Ceres (external) semantics restated, Ceres 2.1 file names for orientation:
  *   HuberLoss / Corrector             loss_function.cc, corrector.cc
  *   EigenQuaternionParameterization   local_parameterization.cc (x,y,z,w; x+ = dq * x)
