@@ -39,6 +39,13 @@ def test_no_cpu_fallback_without_a_gpu():
     with pytest.raises(_lib.XrbError):
         m.SetDescriptors(0, 1, [[0] * 128])
     assert not _lib.lib().xrb_ba_create(0)
+    # the batched entry points take no handle: they must refuse just as loudly
+    from xrsfm_b200 import pnp, synth
+    b = synth.make_pose_batch(2, seed=1)
+    q0 = b["q"].copy()
+    with pytest.raises(_lib.XrbError, match="CUDA"):
+        pnp.refine_poses(b["offsets"], b["uv"], b["xyz"], b["intr"], b["intr_model"], b["q"], b["t"])
+    assert (b["q"] == q0).all()
 
 
 def test_product_never_imports_the_oracle():
