@@ -4,6 +4,7 @@
 #include "xrsfm_mock.h"
 #include "../../xrsfm_b200/shim/SiftMatchGPU_b200.h"
 #include "../../xrsfm_b200/shim/ba_solver_b200.h"
+#include "../../xrsfm_b200/shim/pnp_b200.h"
 
 int main() {
     // the exact call sequence of CreateSiftGPUMatcher / SiftMatch (feature_processing.cc:53-154)
@@ -65,6 +66,26 @@ int main() {
         for (int i = 0; same && i < 5 * 128; ++i) same = desc[i] == desc2[i];
         std::printf("ftr roundtrip: %s\n", same ? "ok" : xrb_last_error());
         std::remove(path);
+    }
+    {
+        // PoseRefiner (pnp.cc:38-71): queueing is host code; without a GPU Run() reports the failure and leaves the
+        // frame's pose alone (with one, tests/test_shims.py runs the same object through shim_gpu_check)
+        mock::Frame frame;
+        frame.Tcw.q.c = {{0, 0, 0, 1}};
+        frame.Tcw.t = {{0.5, -0.25, 2.0}};
+        frame.points = {{{100, 50}}, {{200, 80}}, {{640, 190}}, {{900, 300}}};
+        mock::CameraT cam;
+        cam.model_id_ = 2, cam.params_ = {718.856, 607.19, 185.22, -0.02};
+        std::vector<std::pair<int, int>> ids = {{0, 7}, {2, 9}, {3, 4}};
+        std::vector<mock::Vec3> p3d = {{{1, 2, 10}}, {{0, 0, 12}}, {{3, 1, 9}}};
+        std::vector<char> mask = {1, 0, 1};
+        xrsfm_b200::PoseRefiner<mock::Frame> refiner(0);
+        refiner.Add(frame, cam, ids, p3d, mask);
+        const size_t queued = refiner.size();
+        const int rc = refiner.Run(false);
+        const bool untouched = frame.Tcw.t.v[0] == 0.5 && frame.Tcw.t.v[2] == 2.0 && frame.Tcw.q.c.v[3] == 1.0;
+        std::printf("pose: queued=%zu max_it=%d status_ok=%d untouched=%d\n", queued, refiner.options.max_iterations,
+                    rc == XRB_OK, (int)untouched);
     }
     return 0;
 }

@@ -20,6 +20,12 @@ def test_shims_compile_link_and_run(tmp_path):
     # new frame, small angle), point 1 constant (angle > 5), point 2 constant (not seen by the new frame)
     assert "lba: cams=4 obs=11 pts=3 fixed_t=1000 fixed_pts=011" in out
     assert "lba2: fixed_t=0011" in out
+    # PoseRefiner queues on the host; on this GPU-less box Run() fails loudly and leaves the pose alone
+    import torch
+    if not torch.cuda.is_available():
+        assert "pose: queued=1 max_it=10 status_ok=0 untouched=1" in out
+    else:
+        assert "pose: queued=1 max_it=10 status_ok=1" in out
 
 
 # ------------------------------------------------------------------------------------------
